@@ -1522,7 +1522,8 @@ EXPORT int32_t ora_collide_test(ora_context* ctx, int32_t species, int32_t table
 
 /* Test hook: n uniforms of the stream (uid, domain 0, seed, step) starting at draw index 0, and
  * the raw Philox block for KAT checks. */
-EXPORT int32_t ora_rng_test(uint64_t uid, uint64_t seed, uint32_t step, int32_t n, double* out) {
+EXPORT int32_t ora_rng_test(ora_context* ctx, uint64_t uid, uint64_t seed, uint32_t step, int32_t n, double* out) {
+    (void)ctx;
     rng_t g;
     rng_init(&g, uid, DOM_COLLISION, seed, step);
     for (int i = 0; i < n; i++) out[i] = rng_u(&g);

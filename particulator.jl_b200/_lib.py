@@ -101,10 +101,11 @@ _SIGS = {
     "collision_counts": (C.c_int32, [_vp, C.c_int32, _i64p, C.c_int32]),
     "wall_records": (C.c_int64, [_vp, C.c_int32, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32]),
     "collide_test": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_uint64, _dp]),
+    "rng_test": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, _dp]),
 }
 
 #: every symbol include/particulator_b200.h declares (suffix after the prefix)
-ABI_SYMBOLS = sorted(list(_SIGS) + ["rng_test"])
+ABI_SYMBOLS = sorted(_SIGS)
 
 
 class PtlError(RuntimeError):

@@ -133,6 +133,11 @@ class Context:
         self.check(rc, "table_eval")
         return rates, bound
 
+    def rng_test(self, uid, seed, step, n):
+        out = np.zeros(n)
+        self.check(self.backend.rng_test(self.h, int(uid), int(seed), int(step), n, dptr(out)), "rng_test")
+        return out
+
     def collide_test(self, species, tab, j, p3, uid0=1):
         tid = self.table(tab)
         p3 = as_f64(p3).reshape(-1, 3)

@@ -1,0 +1,276 @@
+// ptl_advance.cuh — K1: the fused advance kernel (one specialisation per species).
+//
+// Replaces, for one population and one pass of advance1! (mixed_population.jl:56-93):
+//   advance_init!/setr!  (mixed_population.jl:97-110, collisions.jl:63-74)      [FIRST pass only]
+//   the per-particle sub-step loop (mixed_population.jl:61-88)
+//   advance_particle (pusher.jl:41-76), onadvance of WallCallback (callback.jl:167-184)
+//   do_one_collision! (collisions.jl:142-199), collide (9 processes + LXCat kinds), apply! (:83-133)
+//   add_particle! (population.jl:103-113) with warp-aggregated atomic appends.
+//
+// Mapping: persistent warps; each warp claims tiles of 32 consecutive rows from a global tile
+// counter (dynamic load balance at warp granularity — the sub-step count per particle varies by
+// >10x with energy), one particle per lane, state in registers for the whole dt, every column
+// access of a warp is one contiguous 256-byte span.  The Chebyshev rate table of the species
+// (<= 12 KB) is staged once per block in shared memory.
+#pragma once
+#include "ptl_physics.cuh"
+
+namespace ptl {
+
+constexpr int ADV_THREADS = 128;
+
+struct SmemTable {
+    const double* rate;        // [order, nprocs, k+1] (cheb) in shared memory, or global pointer (linear)
+    const double* ratebound;   // [order, k+1]
+    const ptl_process_desc* procs;
+};
+
+// add_particle!(popl, state): population.jl:103-113 + setr! of the newborn (collisions.jl:104,118,128,132)
+__device__ __forceinline__ void add_particle(const AdvanceParams& P, int sp, Vec3 x, Vec3 p, double w, double t, double s, uint64_t uid) {
+    const PopView& Q = P.pop[sp];
+    if (!Q.present) return;
+    double eng = kinenergy_rt(sp, p);
+    if (eng <= Q.energy_cut) return;
+    // warp-aggregated append: lanes of the converged group that target the same population share one atomic
+    unsigned grp = __match_any_sync(__activemask(), sp);
+    int leader = __ffs(grp) - 1;
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(Q.n, (unsigned long long)__popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    long long slot = (long long)base + __popc(grp & ((1u << lane) - 1));
+    if (lane == leader) atomicAdd(P.births, (unsigned long long)__popc(grp));
+    if (slot >= Q.capacity) {   // @assert n < length(particles)  population.jl:107
+        atomicOr(P.flags, PTL_ERR_CAPACITY_OVERFLOW);
+        return;
+    }
+    Q.col[COL_X0][slot] = x.x; Q.col[COL_X1][slot] = x.y; Q.col[COL_X2][slot] = x.z;
+    Q.col[COL_P0][slot] = p.x; Q.col[COL_P1][slot] = p.y; Q.col[COL_P2][slot] = p.z;
+    Q.col[COL_W][slot] = w; Q.col[COL_T][slot] = t; Q.col[COL_S][slot] = s;
+    Q.col[COL_R][slot] = ratebound_global(P.tab[sp], eng, P.flags);
+    Q.active[slot] = 1;
+    Q.uid[slot] = uid;
+}
+
+template <int SP>
+__device__ __forceinline__ double own_ratebound(const AdvanceParams& P, const SmemTable& S, double eng) {
+    const TableView& T = P.tab[SP];
+    if (T.kind == 0) {
+        Pre pre = precheb(eng, T.k, T.xmax);
+        if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+        return chebsum(S.ratebound + T.order * pre.i, pre, T.order);
+    }
+    return T.maxrate;
+}
+
+// setr!: collisions.jl:63-74
+template <int SP>
+__device__ __forceinline__ double setr(const AdvanceParams& P, const SmemTable& S, Vec3 p) {
+    double eng = kinenergy<SP>(p);
+    if (eng < P.pop[SP].energy_cut) return 0.0;
+    return own_ratebound<SP>(P, S, eng);
+}
+
+template <int SP, bool FIRST, bool CB>
+__global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                         unsigned long long* tile_counter) {
+    extern __shared__ double smem[];
+    const TableView& T = P.tab[SP];
+    const PopView& Q = P.pop[SP];
+    SmemTable S;
+    if (T.kind == 0) {
+        int nrate = T.order * T.nprocs * (T.k + 1), nrb = T.order * (T.k + 1);
+        int nproc_dbl = (T.nprocs * (int)sizeof(ptl_process_desc)) / 8;
+        for (int q = threadIdx.x; q < nrate; q += blockDim.x) smem[q] = T.rate[q];
+        for (int q = threadIdx.x; q < nrb; q += blockDim.x) smem[nrate + q] = T.ratebound[q];
+        const double* pd = reinterpret_cast<const double*>(T.procs);
+        for (int q = threadIdx.x; q < nproc_dbl; q += blockDim.x) smem[nrate + nrb + q] = pd[q];
+        S.rate = smem;
+        S.ratebound = smem + nrate;
+        S.procs = reinterpret_cast<const ptl_process_desc*>(smem + nrate + nrb);
+    } else {
+        int nproc_dbl = (T.nprocs * (int)sizeof(ptl_process_desc)) / 8;
+        const double* pd = reinterpret_cast<const double*>(T.procs);
+        for (int q = threadIdx.x; q < nproc_dbl; q += blockDim.x) smem[q] = pd[q];
+        S.rate = T.rate;
+        S.ratebound = nullptr;
+        S.procs = reinterpret_cast<const ptl_process_desc*>(smem);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const RngCtx rc = {P.step, P.seed_lo, P.seed_hi};
+    const double cut = Q.energy_cut;
+    unsigned long long nsub = 0;
+
+    for (;;) {
+        long long tile = 0;
+        if (lane == 0) tile = (long long)atomicAdd(tile_counter, 1ULL);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        long long base = i0 + tile * 32;
+        if (base >= i1) break;
+        long long i = base + lane;
+        if (i >= i1) continue;
+        if (!Q.active[i]) continue;    // l.active || continue   mixed_population.jl:63
+
+        Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
+        Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+        double w = Q.col[COL_W][i], t = Q.col[COL_T][i], s = Q.col[COL_S][i];
+        double r = FIRST ? setr<SP>(P, S, p) : Q.col[COL_R][i];   // advance_init!  mixed_population.jl:97-110
+        uint64_t uid = Q.uid[i];
+        Rng rng;
+        rng.init(uid, DOM_COLLISION);
+        bool act = true;
+
+        double trem = P.tfinal - t;                         // :65
+        while (trem > DBL_EPS && act) {                     // :66
+            double tnext = s / r;                           // :67  (r == 0 -> Inf -> free flight)
+            bool collides = trem > tnext;                   // :68
+            double dt = collides ? tnext : trem;
+            if (!collides) s -= dt * r;                     // :74
+            Vec3 xo = x, po = p;
+            double wo = w, to = t;
+            push<SP>(P, x, p, t, dt);                       // :77
+            if (CB) {                                       // onadvance(WallCallback)  callback.jl:167-184
+                for (int k = 0; k < P.cb.nwalls; k++) {
+                    const ptl_wall_desc& wd = P.cb.wall[k];
+                    if (wd.species != SP) continue;
+                    double xoc = wd.coord == 0 ? xo.x : (wd.coord == 1 ? xo.y : xo.z);
+                    double xnc = wd.coord == 0 ? x.x : (wd.coord == 1 ? x.y : x.z);
+                    if (xoc < wd.v && wd.v < xnc) {
+                        double f = (wd.v - xoc) / (xnc - xoc);
+                        rng.skip();   // lincomb builds a state with the 4-arg ctor: one discarded s draw (electron.jl:127-132)
+                        const WallBuf& W = P.wall[k];
+                        unsigned long long slot = atomicAdd(W.n, 1ULL);
+                        if ((long long)slot < W.capacity) {
+                            W.col[0][slot] = x.x * f + xo.x * (1 - f); W.col[1][slot] = x.y * f + xo.y * (1 - f); W.col[2][slot] = x.z * f + xo.z * (1 - f);
+                            W.col[3][slot] = p.x * f + po.x * (1 - f); W.col[4][slot] = p.y * f + po.y * (1 - f); W.col[5][slot] = p.z * f + po.z * (1 - f);
+                            W.col[6][slot] = w * f + wo * (1 - f);
+                            W.col[7][slot] = t * f + to * (1 - f);
+                        } else {
+                            atomicOr(P.flags, PTL_ERR_CAPACITY_OVERFLOW);
+                        }
+                        if (wd.drop) act = false;
+                    }
+                }
+            }
+            if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
+                double eng;
+                if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {   // :148-151
+                    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
+                    if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+                    double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;                     // :154
+                    int jsel = -1;
+                    const int np = T.nprocs;
+                    for (int j = 0; j < np; j++) {          // :166-180
+                        double nu = (T.kind == 0) ? chebsum(S.rate + T.order * (j + np * pre.i), pre, T.order)
+                                                  : linear_rate(S.rate, np, j, pre);
+                        if (nu > xi) { jsel = j; break; }
+                        xi -= nu;
+                    }
+                    Outcome o;
+                    o.kind = OUT_NULL;
+                    if (jsel >= 0) {
+                        collide<SP>(rng, rc, P, S.procs[jsel], p, eng, o);
+                    } else if (!(xi >= 0)) {
+                        atomicOr(P.flags, PTL_ERR_RATE_BOUND_VIOLATED);     // :186
+                    }
+                    if (CB && P.cb.count_collisions) atomicAdd(T.counts + (jsel >= 0 ? jsel : np), 1ULL);
+                    // apply!: collisions.jl:83-133
+                    switch (o.kind) {
+                    case OUT_NULL:
+                        r = setr<SP>(P, S, p);
+                        s = -log(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                        break;
+                    case OUT_STATE_CHANGE:
+                        p = o.p1; s = o.s1; r = setr<SP>(P, S, p);
+                        break;
+                    case OUT_NEW_PARTICLE: {
+                        p = o.p1; s = o.s1; r = setr<SP>(P, S, p);
+                        uint64_t cu[2];
+                        child_uids(uid, rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                        add_particle(P, o.sp2, x, o.p2, w, t, o.s2, cu[0]);
+                        break;
+                    }
+                    case OUT_REMOVE: act = false; break;
+                    case OUT_REPLACE: {
+                        act = false;
+                        uint64_t cu[2];
+                        child_uids(uid, rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                        add_particle(P, o.sp2, x, o.p2, w, t, o.s2, cu[0]);
+                        break;
+                    }
+                    case OUT_REPLACE_PAIR: {
+                        act = false;
+                        uint64_t cu[2];
+                        child_uids(uid, rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                        add_particle(P, o.sp2, x, o.p2, w, t, o.s2, cu[0]);
+                        add_particle(P, o.sp3, x, o.p3, w, t, o.s3, cu[1]);
+                        break;
+                    }
+                    }
+                }
+            }
+            trem -= dt;                                      // :86
+            nsub++;
+        }
+
+        Q.col[COL_X0][i] = x.x; Q.col[COL_X1][i] = x.y; Q.col[COL_X2][i] = x.z;
+        Q.col[COL_P0][i] = p.x; Q.col[COL_P1][i] = p.y; Q.col[COL_P2][i] = p.z;
+        Q.col[COL_T][i] = t; Q.col[COL_S][i] = s; Q.col[COL_R][i] = r;
+        if (!act) Q.active[i] = 0;
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
+    if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+}
+
+// init!(mpopl) / advance_init!: setr! on all actives (mixed_population.jl:20-35)
+template <int SP>
+__global__ void k_init_r(const __grid_constant__ AdvanceParams P, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PopView& Q = P.pop[SP];
+    if (!Q.active[i]) return;
+    Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+    double eng = kinenergy<SP>(p);
+    Q.col[COL_R][i] = eng < Q.energy_cut ? 0.0 : ratebound_global(P.tab[SP], eng, P.flags);
+}
+
+// bit-exact tier entry point: presample + rate(j) + ratebound for n energies
+__global__ void k_table_eval(TableView T, long long n, const double* __restrict__ energy, double* __restrict__ rates,
+                             double* __restrict__ bound, int* flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double eng = energy[i];
+    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);
+    for (int j = 0; j < T.nprocs; j++)
+        rates[j + (size_t)T.nprocs * i] = (T.kind == 0) ? chebsum(T.rate + (size_t)T.order * (j + (size_t)T.nprocs * pre.i), pre, T.order)
+                                                        : linear_rate(T.rate, T.nprocs, j, pre);
+    bound[i] = ratebound_global(T, eng, flags);
+}
+
+// deterministic replay of single collide() events (test entry point ptl_collide_test)
+template <int SP>
+__global__ void k_collide_test(const __grid_constant__ AdvanceParams P, TableView T, int j, long long n, const double* __restrict__ p3,
+                               unsigned long long uid0, double* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RngCtx rc = {P.step, P.seed_lo, P.seed_hi};
+    Rng rng;
+    rng.init(uid0 + (unsigned long long)i, DOM_COLLISION);
+    Vec3 p = {p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]};
+    Outcome o;
+    o.kind = OUT_NULL; o.sp2 = o.sp3 = 0;
+    o.p1 = o.p2 = o.p3 = {0, 0, 0};
+    o.s1 = o.s2 = o.s3 = 0;
+    collide<SP>(rng, rc, P, T.procs[j], p, kinenergy<SP>(p), o);
+    double* r = out + 24 * i;
+    for (int q = 0; q < 24; q++) r[q] = 0;
+    r[0] = o.kind; r[3] = rng.idx;
+    if (o.kind == OUT_STATE_CHANGE || o.kind == OUT_NEW_PARTICLE) { r[4] = o.p1.x; r[5] = o.p1.y; r[6] = o.p1.z; r[7] = o.s1; }
+    if (o.kind == OUT_NEW_PARTICLE || o.kind == OUT_REPLACE || o.kind == OUT_REPLACE_PAIR) { r[1] = o.sp2; r[8] = o.p2.x; r[9] = o.p2.y; r[10] = o.p2.z; r[11] = o.s2; }
+    if (o.kind == OUT_REPLACE_PAIR) { r[2] = o.sp3; r[12] = o.p3.x; r[13] = o.p3.y; r[14] = o.p3.z; r[15] = o.s3; }
+}
+
+}  // namespace ptl

@@ -1,0 +1,910 @@
+// ptl_api.cu — the C ABI of include/particulator_b200.h: context, device-resident stores, table
+// upload, and the host-side launch logic of every kernel (advance pass loop, compaction, diagnostics).
+// Plain C signatures only; no torch / C++ types cross the boundary.  There is NO CPU fallback: a
+// context can only be created on a compute-capability-10.x device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ptl_advance.cuh"
+#include "ptl_store.cuh"
+
+using namespace ptl;
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct DeviceScalars {            // one small device block mirrored in pinned host memory
+    int flags;
+    int _pad;
+    unsigned long long substeps, births, tile_counter, total, nmoves;
+    unsigned long long pop_n[16];
+    unsigned long long wall_n[PTL_MAX_WALLS];
+    double diag[DIAG_NVAL];
+};
+
+struct Table {
+    TableView v{};
+    std::vector<ptl_process_desc> procs;
+    double *d_rate = nullptr, *d_rb = nullptr;
+    ptl_process_desc* d_procs = nullptr;
+    unsigned long long* d_counts = nullptr;
+    size_t smem_bytes = 0;
+};
+
+struct Pop {
+    PopView v{};
+    void* block = nullptr;
+    long long iup = 0;
+    int table = -1;
+    int slot = -1;                // index into DeviceScalars.pop_n
+    bool alive = false;
+};
+
+struct MultiPop {
+    std::vector<int> pops;
+    int by_species[PTL_NSPECIES];
+};
+
+struct Sb { SbView v{}; };
+struct ChebLoss { ChebLossView v{}; };
+
+struct Wall {
+    WallBuf b{};
+    void* block = nullptr;
+};
+
+}  // namespace
+
+struct ptl_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::vector<Table> tables;
+    std::vector<Pop> pops;
+    std::vector<Sb> sbs;
+    std::vector<ChebLoss> cls;
+    std::vector<MultiPop> mps;
+    Wall walls[PTL_MAX_WALLS];
+    DeviceScalars* d_sc = nullptr;
+    DeviceScalars* h_sc = nullptr;     // pinned
+    uint64_t seed = 0;
+    uint32_t step = 0;
+    uint64_t next_uid = 1;
+    ptl_advance_stats stats{};
+    std::string err;
+    // scratch
+    void* stage[2] = {nullptr, nullptr};
+    size_t stage_rows = 0;
+    unsigned int* d_tile_counts = nullptr;
+    unsigned long long* d_tile_offsets = nullptr;
+    size_t tiles_cap = 0;
+    long long *d_holes = nullptr, *d_tails = nullptr;
+    size_t moves_cap = 0;
+    double* d_partial = nullptr;
+    int partial_blocks = 0;
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+};
+
+namespace {
+
+bool cuda_ok(ptl_context* ctx, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define CK(call) do { if (!cuda_ok(ctx, (call), #call)) return PTL_ECUDA; } while (0)
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+int32_t sync_scalars(ptl_context* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+Pop* get_pop(ptl_context* ctx, int32_t pop) {
+    if (!ctx || pop < 0 || pop >= (int)ctx->pops.size() || !ctx->pops[pop].alive) return nullptr;
+    return &ctx->pops[pop];
+}
+
+unsigned long long* dev_n(ptl_context* ctx, const Pop& P) { return &ctx->d_sc->pop_n[P.slot]; }
+
+// read popl.n from the device (clamped to capacity; overflow raises the sticky flag)
+int32_t read_n(ptl_context* ctx, Pop& P, long long* out) {
+    int32_t rc = sync_scalars(ctx);
+    if (rc) return rc;
+    long long n = (long long)ctx->h_sc->pop_n[P.slot];
+    if (n > P.v.capacity) {
+        n = P.v.capacity;
+        unsigned long long nn = (unsigned long long)n;
+        CK(cudaMemcpyAsync(dev_n(ctx, P), &nn, sizeof(nn), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = n;
+    return 0;
+}
+
+int32_t set_n(ptl_context* ctx, Pop& P, long long n) {
+    unsigned long long nn = (unsigned long long)n;
+    ctx->h_sc->pop_n[P.slot] = nn;
+    CK(cudaMemcpyAsync(dev_n(ctx, P), &ctx->h_sc->pop_n[P.slot], sizeof(nn), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int32_t ensure_stage(ptl_context* ctx) {
+    const size_t rows = (size_t)1 << 22;   // 4 Mi rows x 24 B = 96 MiB per staging buffer
+    if (ctx->stage_rows >= rows) return 0;
+    for (int b = 0; b < 2; b++) CK(cudaMalloc(&ctx->stage[b], rows * 3 * sizeof(double)));
+    ctx->stage_rows = rows;
+    return 0;
+}
+
+int32_t ensure_tmp(ptl_context* ctx, size_t bytes) {
+    if (ctx->tmp_bytes >= bytes) return 0;
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    ctx->d_tmp = nullptr; ctx->tmp_bytes = 0;
+    CK(cudaMalloc(&ctx->d_tmp, bytes));
+    ctx->tmp_bytes = bytes;
+    return 0;
+}
+
+void fill_params(ptl_context* ctx, const MultiPop* mp, AdvanceParams& A) {
+    memset(&A, 0, sizeof(A));
+    for (int s = 0; s < PTL_NSPECIES; s++) {
+        int pi = mp ? mp->by_species[s] : -1;
+        if (pi >= 0) {
+            A.pop[s] = ctx->pops[pi].v;
+            A.pop[s].present = 1;
+            A.tab[s] = ctx->tables[ctx->pops[pi].table].v;
+        }
+    }
+    for (size_t i = 0; i < ctx->sbs.size() && i < (size_t)MAX_SB; i++) A.sb[i] = ctx->sbs[i].v;
+    for (size_t i = 0; i < ctx->cls.size() && i < (size_t)MAX_CHEBLOSS; i++) A.cl[i] = ctx->cls[i].v;
+    for (int k = 0; k < PTL_MAX_WALLS; k++) A.wall[k] = ctx->walls[k].b;
+    A.seed_lo = (uint32_t)ctx->seed;
+    A.seed_hi = (uint32_t)(ctx->seed >> 32);
+    A.step = ctx->step;
+    A.flags = &ctx->d_sc->flags;
+    A.substeps = &ctx->d_sc->substeps;
+    A.births = &ctx->d_sc->births;
+}
+
+template <int SP, bool FIRST, bool CB>
+int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t smem) {
+    auto kern = k_advance<SP, FIRST, CB>;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        configured = true;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, ADV_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long tiles = (i1 - i0 + 31) / 32;
+    long long want = (tiles + (ADV_THREADS / 32) - 1) / (ADV_THREADS / 32);
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
+
+template <int SP>
+int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
+    if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem);
+    return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem);
+}
+
+int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
+    switch (species) {
+    case PTL_ELECTRON: return launch_advance_s<PTL_ELECTRON>(ctx, A, i0, i1, first, cb, smem);
+    case PTL_PHOTON: return launch_advance_s<PTL_PHOTON>(ctx, A, i0, i1, first, cb, smem);
+    case PTL_POSITRON: return launch_advance_s<PTL_POSITRON>(ctx, A, i0, i1, first, cb, smem);
+    case PTL_SLOW_ELECTRON: return launch_advance_s<PTL_SLOW_ELECTRON>(ctx, A, i0, i1, first, cb, smem);
+    }
+    return PTL_EINVAL;
+}
+
+#define DISPATCH_SPECIES(sp, ...)                                                   \
+    switch (sp) {                                                                   \
+    case PTL_ELECTRON: { constexpr int SP = PTL_ELECTRON; __VA_ARGS__; break; }     \
+    case PTL_PHOTON: { constexpr int SP = PTL_PHOTON; __VA_ARGS__; break; }         \
+    case PTL_POSITRON: { constexpr int SP = PTL_POSITRON; __VA_ARGS__; break; }     \
+    default: { constexpr int SP = PTL_SLOW_ELECTRON; __VA_ARGS__; break; }          \
+    }
+
+unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+EXPORT int32_t ptl_abi_version(void) { return PTL_ABI_VERSION; }
+
+EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** out) {
+    if (!out) return PTL_EINVAL;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return PTL_ENODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PTL_ENODEVICE;
+    if (prop.major != 10) return PTL_ENODEVICE;   // sm_100a cubin only: no fallback of any kind
+    if (cudaSetDevice(device) != cudaSuccess) return PTL_ECUDA;
+    ptl_context* ctx = new ptl_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PTL_ECUDA; }
+        ctx->own_stream = true;
+    }
+    if (cudaMalloc(&ctx->d_sc, sizeof(DeviceScalars)) != cudaSuccess || cudaMallocHost(&ctx->h_sc, sizeof(DeviceScalars)) != cudaSuccess) {
+        delete ctx;
+        return PTL_ENOMEM;
+    }
+    cudaMemsetAsync(ctx->d_sc, 0, sizeof(DeviceScalars), ctx->stream);
+    memset(ctx->h_sc, 0, sizeof(DeviceScalars));
+    ctx->partial_blocks = ctx->sm_count * 8;
+    if (cudaMalloc(&ctx->d_partial, sizeof(double) * DIAG_NVAL * ctx->partial_blocks) != cudaSuccess) { delete ctx; return PTL_ENOMEM; }
+    cudaStreamSynchronize(ctx->stream);
+    *out = ctx;
+    return 0;
+}
+
+EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
+    if (!ctx) return PTL_EINVAL;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_procs); cudaFree(t.d_counts); }
+    for (auto& p : ctx->pops) if (p.block) cudaFree(p.block);
+    for (auto& s : ctx->sbs) { cudaFree((void*)s.v.log_energy); cudaFree((void*)s.v.data); }
+    for (auto& c : ctx->cls) { cudaFree((void*)c.v.ec); cudaFree((void*)c.v.pc); }
+    for (auto& w : ctx->walls) if (w.block) cudaFree(w.block);
+    for (int b = 0; b < 2; b++) if (ctx->stage[b]) cudaFree(ctx->stage[b]);
+    cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets); cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp);
+    cudaFree(ctx->d_sc);
+    cudaFreeHost(ctx->h_sc);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+EXPORT const char* ptl_last_error(ptl_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+EXPORT int32_t ptl_error_flags(ptl_context* ctx, int32_t clear) {
+    if (!ctx) return PTL_EINVAL;
+    int32_t rc = sync_scalars(ctx);
+    if (rc) return rc;
+    int f = ctx->h_sc->flags;
+    if (clear) { CK(cudaMemsetAsync(&ctx->d_sc->flags, 0, sizeof(int), ctx->stream)); }
+    return f;
+}
+
+EXPORT int32_t ptl_synchronize(ptl_context* ctx) {
+    if (!ctx) return PTL_EINVAL;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+EXPORT int32_t ptl_set_rng(ptl_context* ctx, uint64_t seed, uint32_t step) {
+    if (!ctx) return PTL_EINVAL;
+    ctx->seed = seed; ctx->step = step;
+    return 0;
+}
+EXPORT int32_t ptl_get_rng(ptl_context* ctx, uint64_t* seed, uint32_t* step) {
+    if (!ctx) return PTL_EINVAL;
+    if (seed) *seed = ctx->seed;
+    if (step) *step = ctx->step;
+    return 0;
+}
+
+// =====================================================================================================
+// tables
+// =====================================================================================================
+namespace {
+int32_t upload_doubles(ptl_context* ctx, const double* src, size_t n, double** dst) {
+    CK(cudaMalloc(dst, sizeof(double) * (n ? n : 1)));
+    if (n) CK(cudaMemcpyAsync(*dst, src, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int32_t upload_procs(ptl_context* ctx, Table& T, const ptl_process_desc* procs, int nprocs) {
+    T.procs.assign(procs, procs + nprocs);
+    for (auto& p : T.procs) {
+        if (p.kind == PTL_PROC_COULOMB) p.par[1] = pow(p.par[0], -1.0 / 3.0);   // Z^(-1//3), relativistic_coulomb.jl:14
+        if (p.kind == PTL_PROC_SELTZER && (p.aux < 0 || p.aux >= (int)ctx->sbs.size())) return PTL_EHANDLE;
+    }
+    CK(cudaMalloc(&T.d_procs, sizeof(ptl_process_desc) * (nprocs ? nprocs : 1)));
+    if (nprocs) CK(cudaMemcpyAsync(T.d_procs, T.procs.data(), sizeof(ptl_process_desc) * nprocs, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMalloc(&T.d_counts, sizeof(unsigned long long) * (nprocs + 1)));
+    CK(cudaMemsetAsync(T.d_counts, 0, sizeof(unsigned long long) * (nprocs + 1), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    T.v.procs = T.d_procs;
+    T.v.counts = T.d_counts;
+    T.v.nprocs = nprocs;
+    return 0;
+}
+}  // namespace
+
+EXPORT int32_t ptl_sb_table_create(ptl_context* ctx, int32_t ncum, int32_t nE, const double* log_energy, const double* data) {
+    if (!ctx || ncum < 2 || nE < 2 || !log_energy || !data) return PTL_EINVAL;
+    if (ctx->sbs.size() >= (size_t)MAX_SB) return PTL_ENOMEM;
+    Sb s;
+    s.v.ncum = ncum; s.v.nE = nE;
+    double *dl = nullptr, *dd = nullptr;
+    int32_t rc = upload_doubles(ctx, log_energy, nE, &dl); if (rc) return rc;
+    rc = upload_doubles(ctx, data, (size_t)ncum * nE, &dd); if (rc) return rc;
+    s.v.log_energy = dl; s.v.data = dd;
+    ctx->sbs.push_back(s);
+    return (int32_t)ctx->sbs.size() - 1;
+}
+
+EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t nprocs, int32_t k, double xmax, const double* rate,
+                                     const double* ratebound, const ptl_process_desc* procs) {
+    if (!ctx || order < 1 || order > MAX_ORDER || nprocs < 0 || nprocs > PTL_MAX_PROCS || k < 1 || !(xmax > 0)) return PTL_EINVAL;
+    Table T;
+    T.v.kind = 0; T.v.order = order; T.v.k = k; T.v.xmax = xmax;
+    int32_t rc = upload_doubles(ctx, rate, (size_t)order * nprocs * (k + 1), &T.d_rate); if (rc) return rc;
+    rc = upload_doubles(ctx, ratebound, (size_t)order * (k + 1), &T.d_rb); if (rc) return rc;
+    T.v.rate = T.d_rate; T.v.ratebound = T.d_rb;
+    rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
+    T.smem_bytes = sizeof(double) * ((size_t)order * nprocs * (k + 1) + (size_t)order * (k + 1)) + sizeof(ptl_process_desc) * nprocs;
+    if (T.smem_bytes > 60 * 1024) { ctx->err = "Chebyshev table too large for shared memory"; return PTL_EINVAL; }
+    ctx->tables.push_back(T);
+    return (int32_t)ctx->tables.size() - 1;
+}
+
+EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, double L1, double L2, int32_t nE, int32_t nprocs,
+                                       const double* rate, double maxrate, const ptl_process_desc* procs) {
+    if (!ctx || nE < 2 || nprocs < 0 || nprocs > PTL_MAX_PROCS || (grid_kind != 0 && grid_kind != 1)) return PTL_EINVAL;
+    Table T;
+    T.v.kind = 1; T.v.grid_kind = grid_kind; T.v.L1 = L1; T.v.L2 = L2; T.v.nE = nE; T.v.maxrate = maxrate;
+    int32_t rc = upload_doubles(ctx, rate, (size_t)nprocs * nE, &T.d_rate); if (rc) return rc;
+    T.v.rate = T.d_rate;
+    rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
+    T.smem_bytes = sizeof(ptl_process_desc) * nprocs;
+    ctx->tables.push_back(T);
+    return (int32_t)ctx->tables.size() - 1;
+}
+
+EXPORT int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, double xmax, const double* ec, const double* pc) {
+    if (!ctx || order < 1 || order > MAX_ORDER || k < 1) return PTL_EINVAL;
+    if (ctx->cls.size() >= (size_t)MAX_CHEBLOSS) return PTL_ENOMEM;
+    ChebLoss c;
+    c.v.order = order; c.v.k = k; c.v.xmax = xmax;
+    double *de = nullptr, *dp = nullptr;
+    int32_t rc = upload_doubles(ctx, ec, (size_t)order * (k + 1), &de); if (rc) return rc;
+    rc = upload_doubles(ctx, pc, (size_t)order * (k + 1), &dp); if (rc) return rc;
+    c.v.ec = de; c.v.pc = dp;
+    ctx->cls.push_back(c);
+    return (int32_t)ctx->cls.size() - 1;
+}
+
+EXPORT int32_t ptl_table_eval(ptl_context* ctx, int32_t table, int64_t n, const double* energy, double* rates_out, double* bound_out) {
+    if (!ctx || table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
+    if (n <= 0) return 0;
+    const Table& T = ctx->tables[table];
+    size_t np = (size_t)(T.v.nprocs > 0 ? T.v.nprocs : 1);
+    int32_t rc = ensure_tmp(ctx, sizeof(double) * (size_t)n * (np + 2)); if (rc) return rc;
+    double* d_e = (double*)ctx->d_tmp;
+    double* d_b = d_e + n;
+    double* d_r = d_b + n;
+    CK(cudaMemcpyAsync(d_e, energy, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_table_eval<<<grid_for(n, 128), 128, 0, ctx->stream>>>(T.v, n, d_e, d_r, d_b, &ctx->d_sc->flags);
+    CK(cudaGetLastError());
+    if (T.v.nprocs) CK(cudaMemcpyAsync(rates_out, d_r, sizeof(double) * n * T.v.nprocs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(bound_out, d_b, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// =====================================================================================================
+// populations
+// =====================================================================================================
+EXPORT int32_t ptl_population_create(ptl_context* ctx, int32_t species, int64_t capacity, double energy_cut, int32_t table) {
+    if (!ctx || species < 0 || species >= PTL_NSPECIES || capacity < 1) return PTL_EINVAL;
+    if (table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
+    if (ctx->pops.size() >= 16) return PTL_ENOMEM;
+    Pop P;
+    size_t colb = align256(sizeof(double) * (size_t)capacity);
+    size_t actb = align256((size_t)capacity);
+    size_t total = colb * 11 + actb;
+    if (cudaMalloc(&P.block, total) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMalloc of the particle store failed"; return PTL_ENOMEM; }
+    char* base = (char*)P.block;
+    for (int c = 0; c < 10; c++) P.v.col[c] = (double*)(base + colb * c);
+    P.v.uid = (uint64_t*)(base + colb * 10);
+    P.v.active = (uint8_t*)(base + colb * 11);
+    P.v.capacity = capacity;
+    P.v.energy_cut = energy_cut;
+    P.v.species = species;
+    P.v.present = 1;
+    P.table = table;
+    P.slot = (int)ctx->pops.size();
+    P.v.n = &ctx->d_sc->pop_n[P.slot];
+    P.alive = true;
+    CK(cudaMemsetAsync(P.v.n, 0, sizeof(unsigned long long), ctx->stream));
+    ctx->pops.push_back(P);
+    return (int32_t)ctx->pops.size() - 1;
+}
+
+EXPORT int32_t ptl_population_destroy(ptl_context* ctx, int32_t pop) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(P->block);
+    P->block = nullptr;
+    P->alive = false;
+    return 0;
+}
+
+EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, const double* x3, const double* p3, const double* w,
+                                     const double* t, const double* s, const double* r, const uint8_t* active, const uint64_t* uid) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    if (n < 0 || n > P->v.capacity) return PTL_EINVAL;
+    if (n > 0 && (!x3 || !p3 || !w || !t || !s || !r || !active)) return PTL_EINVAL;
+    int32_t rc = ensure_stage(ctx); if (rc) return rc;
+    // x, p: host xyz-interleaved -> planar columns, chunked through two staging buffers
+    int b = 0;
+    for (int which = 0; which < 2; which++) {
+        const double* src = which == 0 ? x3 : p3;
+        int c0 = which == 0 ? COL_X0 : COL_P0;
+        for (long long off = 0; off < n; off += (long long)ctx->stage_rows) {
+            long long m = n - off < (long long)ctx->stage_rows ? n - off : (long long)ctx->stage_rows;
+            CK(cudaMemcpyAsync(ctx->stage[b], src + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+            k_aos3_to_planar<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[b], P->v.col[c0] + off, P->v.col[c0 + 1] + off,
+                                                                        P->v.col[c0 + 2] + off, m);
+            CK(cudaGetLastError());
+            b ^= 1;
+        }
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(P->v.col[COL_W], w, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->v.col[COL_T], t, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->v.col[COL_S], s, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->v.col[COL_R], r, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(P->v.active, active, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        if (uid) {
+            CK(cudaMemcpyAsync(P->v.uid, uid, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            k_fill_uid<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.uid, ctx->next_uid, n);
+            CK(cudaGetLastError());
+        }
+    }
+    ctx->next_uid += (uint64_t)n;
+    P->iup = 0;
+    rc = set_n(ctx, *P, n); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));   // host arrays are only borrowed for the duration of the call
+    return 0;
+}
+
+EXPORT int64_t ptl_population_download(ptl_context* ctx, int32_t pop, int64_t max_n, double* x3, double* p3, double* w, double* t,
+                                       double* s, double* r, uint8_t* active, uint64_t* uid) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (n > max_n) n = max_n;
+    if (n <= 0) return 0;
+    rc = ensure_stage(ctx); if (rc) return rc;
+    int b = 0;
+    for (int which = 0; which < 2; which++) {
+        double* dst = which == 0 ? x3 : p3;
+        if (!dst) continue;
+        int c0 = which == 0 ? COL_X0 : COL_P0;
+        for (long long off = 0; off < n; off += (long long)ctx->stage_rows) {
+            long long m = n - off < (long long)ctx->stage_rows ? n - off : (long long)ctx->stage_rows;
+            k_planar_to_aos3<<<grid_for(m, 256), 256, 0, ctx->stream>>>(P->v.col[c0] + off, P->v.col[c0 + 1] + off, P->v.col[c0 + 2] + off,
+                                                                        (double*)ctx->stage[b], m);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(dst + 3 * off, ctx->stage[b], sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
+            b ^= 1;
+        }
+    }
+    if (w) CK(cudaMemcpyAsync(w, P->v.col[COL_W], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t) CK(cudaMemcpyAsync(t, P->v.col[COL_T], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (s) CK(cudaMemcpyAsync(s, P->v.col[COL_S], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (r) CK(cudaMemcpyAsync(r, P->v.col[COL_R], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (active) CK(cudaMemcpyAsync(active, P->v.active, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uid) CK(cudaMemcpyAsync(uid, P->v.uid, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return n;
+}
+
+EXPORT int64_t ptl_population_n(ptl_context* ctx, int32_t pop) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n);
+    return rc ? rc : n;
+}
+
+EXPORT int64_t ptl_population_capacity(ptl_context* ctx, int32_t pop) {
+    Pop* P = get_pop(ctx, pop);
+    return P ? P->v.capacity : PTL_EHANDLE;
+}
+
+EXPORT int32_t ptl_population_clear(ptl_context* ctx, int32_t pop) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    return set_n(ctx, *P, 0);
+}
+
+EXPORT int32_t ptl_population_set_n(ptl_context* ctx, int32_t pop, int64_t n) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    if (n < 0 || n > P->v.capacity) return PTL_EINVAL;
+    return set_n(ctx, *P, n);
+}
+
+EXPORT void* ptl_population_column_ptr(ptl_context* ctx, int32_t pop, int32_t col) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || col < 0 || col >= NCOLS) return nullptr;
+    if (col < 10) return P->v.col[col];
+    return col == COL_ACTIVE ? (void*)P->v.active : (void*)P->v.uid;
+}
+
+EXPORT int64_t ptl_population_append(ptl_context* ctx, int32_t pop, const double* x3, const double* p3, double w, double t, double s,
+                                     double r, uint64_t uid) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || !x3 || !p3) return PTL_EHANDLE;
+    double p2 = p3[0] * p3[0] + p3[1] * p3[1] + p3[2] * p3[2];
+    double eng = P->v.species == PTL_PHOTON ? sqrt(p2) * CO_C
+               : P->v.species == PTL_SLOW_ELECTRON ? 0.5 * CO_ME * p2
+               : sqrt(CO_MC2 * CO_MC2 + CO_C2 * p2) - CO_MC2;
+    if (eng <= P->v.energy_cut) return -1;   // population.jl:105
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (n >= P->v.capacity) {
+        ctx->h_sc->flags |= PTL_ERR_CAPACITY_OVERFLOW;
+        int f = PTL_ERR_CAPACITY_OVERFLOW;
+        cudaMemcpyAsync(&ctx->d_sc->flags, &f, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        return -1;
+    }
+    double vals[10] = {x3[0], x3[1], x3[2], p3[0], p3[1], p3[2], w, t, s, r};
+    for (int c = 0; c < 10; c++) CK(cudaMemcpyAsync(P->v.col[c] + n, &vals[c], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t one = 1;
+    if (uid == 0) uid = ctx->next_uid++;
+    CK(cudaMemcpyAsync(P->v.active + n, &one, 1, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(P->v.uid + n, &uid, sizeof(uid), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    rc = set_n(ctx, *P, n + 1); if (rc) return rc;
+    return n;
+}
+
+EXPORT int32_t ptl_population_deactivate(ptl_context* ctx, int32_t pop, int64_t i) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (i < 0 || i >= n) return PTL_EINVAL;
+    CK(cudaMemsetAsync(P->v.active + i, 0, 1, ctx->stream));
+    return 0;
+}
+
+// ---- droplow! / repack! ---------------------------------------------------------------------------------
+namespace {
+int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
+    long long n = 0;
+    int32_t rc = read_n(ctx, P, &n); if (rc) return rc;
+    if (n == 0) return 0;
+    long long ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    if ((size_t)ntiles > ctx->tiles_cap) {
+        cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets);
+        size_t cap = (size_t)ntiles + 1024;
+        CK(cudaMalloc(&ctx->d_tile_counts, sizeof(unsigned int) * cap));
+        CK(cudaMalloc(&ctx->d_tile_offsets, sizeof(unsigned long long) * cap));
+        ctx->tiles_cap = cap;
+    }
+    double th = thres == 0 ? P.v.energy_cut : thres;   // population.jl:274
+    DISPATCH_SPECIES(P.v.species, k_flag_count<SP><<<(unsigned)ntiles, CMP_THREADS, 0, ctx->stream>>>(P.v, n, th, do_flag ? 1 : 0, ctx->d_tile_counts));
+    CK(cudaGetLastError());
+    k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_counts, ntiles, ctx->d_tile_offsets, &ctx->d_sc->total);
+    CK(cudaGetLastError());
+    CK(cudaMemsetAsync(&ctx->d_sc->nmoves, 0, sizeof(unsigned long long), ctx->stream));
+    rc = sync_scalars(ctx); if (rc) return rc;
+    long long total = (long long)ctx->h_sc->total;
+    long long max_moves = total < n - total ? total : n - total;
+    if (max_moves > 0) {
+        if ((size_t)max_moves > ctx->moves_cap) {
+            cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
+            size_t cap = (size_t)max_moves + (size_t)max_moves / 4 + 1024;
+            CK(cudaMalloc(&ctx->d_holes, sizeof(long long) * cap));
+            CK(cudaMalloc(&ctx->d_tails, sizeof(long long) * cap));
+            ctx->moves_cap = cap;
+        }
+        k_emit_moves<<<(unsigned)ntiles, CMP_THREADS, 0, ctx->stream>>>(P.v, n, ctx->d_tile_offsets, &ctx->d_sc->total, ctx->d_holes, ctx->d_tails,
+                                                                         &ctx->d_sc->nmoves);
+        CK(cudaGetLastError());
+        k_apply_moves<<<grid_for(max_moves, 256), 256, 0, ctx->stream>>>(P.v, ctx->d_holes, ctx->d_tails, &ctx->d_sc->nmoves);
+        CK(cudaGetLastError());
+    }
+    rc = set_n(ctx, P, total); if (rc) return rc;
+    return total;
+}
+}  // namespace
+
+EXPORT int64_t ptl_droplow(ptl_context* ctx, int32_t pop, double thres) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    return compact(ctx, *P, true, thres);
+}
+
+EXPORT int64_t ptl_repack(ptl_context* ctx, int32_t pop) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    return compact(ctx, *P, false, 0.0);
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------------------
+EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || !out) return PTL_EHANDLE;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    memset(out, 0, sizeof(*out));
+    out->n = n;
+    out->maxenergy = -INFINITY;
+    if (n == 0) return 0;
+    int blocks = (int)((n + DIAG_THREADS - 1) / DIAG_THREADS);
+    if (blocks > ctx->partial_blocks) blocks = ctx->partial_blocks;
+    DISPATCH_SPECIES(P->v.species, k_diag_partial<SP><<<blocks, DIAG_THREADS, 0, ctx->stream>>>(P->v, n, ctx->d_partial));
+    CK(cudaGetLastError());
+    k_diag_final<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, blocks, ctx->d_sc->diag);
+    CK(cudaGetLastError());
+    rc = sync_scalars(ctx); if (rc) return rc;
+    const double* d = ctx->h_sc->diag;
+    out->nactive = (int64_t)llround(d[0]);
+    out->weight = d[1]; out->wenergy = d[2];
+    for (int c = 0; c < 3; c++) { out->wx[c] = d[3 + c]; out->wx2[c] = d[6 + c]; }
+    out->wr2 = d[9];
+    out->maxenergy = d[10];
+    return 0;
+}
+
+EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, double lo, double hi, int32_t nbins, int32_t logscale,
+                             double* out) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || !out || nbins < 1 || nbins > 4096 || !(hi > lo)) return PTL_EINVAL;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    rc = ensure_tmp(ctx, sizeof(double) * nbins); if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_tmp, 0, sizeof(double) * nbins, ctx->stream));
+    if (n > 0) {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+        DISPATCH_SPECIES(P->v.species, k_histogram<SP><<<blocks, 256, sizeof(double) * nbins, ctx->stream>>>(P->v, n, quantity, lo, hi, nbins, logscale,
+                                                                                                             (double*)ctx->d_tmp));
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_tmp, sizeof(double) * nbins, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || !(p > 0)) return PTL_EINVAL;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (n > 0) {
+        k_roulette<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32));
+        CK(cudaGetLastError());
+    }
+    ctx->step++;
+    return 0;
+}
+
+EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
+    Pop* P = get_pop(ctx, pop);
+    if (!P || !(p >= 0)) return PTL_EINVAL;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (n > 0) {
+        k_split<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), &ctx->d_sc->flags);
+        CK(cudaGetLastError());
+    }
+    ctx->step++;
+    rc = read_n(ctx, *P, &n); if (rc) return rc;
+    return ctx->h_sc->flags;
+}
+
+// =====================================================================================================
+// multi-population + advance
+// =====================================================================================================
+EXPORT int32_t ptl_multipop_create(ptl_context* ctx, const int32_t* pops, int32_t count) {
+    if (!ctx || !pops || count < 1 || count > PTL_NSPECIES) return PTL_EINVAL;
+    MultiPop m;
+    for (int s = 0; s < PTL_NSPECIES; s++) m.by_species[s] = -1;
+    for (int i = 0; i < count; i++) {
+        Pop* P = get_pop(ctx, pops[i]);
+        if (!P) return PTL_EHANDLE;
+        if (m.by_species[P->v.species] >= 0) { ctx->err = "two populations of the same species in one MultiPopulation"; return PTL_EINVAL; }
+        m.by_species[P->v.species] = pops[i];
+        m.pops.push_back(pops[i]);
+    }
+    ctx->mps.push_back(m);
+    return (int32_t)ctx->mps.size() - 1;
+}
+
+EXPORT int32_t ptl_init(ptl_context* ctx, int32_t mp) {
+    if (!ctx || mp < 0 || mp >= (int)ctx->mps.size()) return PTL_EHANDLE;
+    const MultiPop& M = ctx->mps[mp];
+    AdvanceParams A;
+    fill_params(ctx, &M, A);
+    int32_t rc = sync_scalars(ctx); if (rc) return rc;
+    for (int pi : M.pops) {
+        Pop& P = ctx->pops[pi];
+        long long n = (long long)ctx->h_sc->pop_n[P.slot];
+        if (n <= 0) continue;
+        DISPATCH_SPECIES(P.v.species, k_init_r<SP><<<grid_for(n, 256), 256, 0, ctx->stream>>>(A, n));
+        CK(cudaGetLastError());
+    }
+    rc = sync_scalars(ctx); if (rc) return rc;
+    return ctx->h_sc->flags;
+}
+
+namespace {
+int32_t ensure_wall(ptl_context* ctx, int k, long long capacity) {
+    Wall& W = ctx->walls[k];
+    if (W.block && W.b.capacity >= capacity) return 0;
+    if (W.block) cudaFree(W.block);
+    size_t colb = align256(sizeof(double) * (size_t)capacity);
+    CK(cudaMalloc(&W.block, colb * 8));
+    for (int c = 0; c < 8; c++) W.b.col[c] = (double*)((char*)W.block + colb * c);
+    W.b.capacity = capacity;
+    W.b.n = &ctx->d_sc->wall_n[k];
+    CK(cudaMemsetAsync(W.b.n, 0, sizeof(unsigned long long), ctx->stream));
+    return 0;
+}
+}  // namespace
+
+EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* pusher, double tfinal, const ptl_callback_desc* cb) {
+    if (!ctx || mp < 0 || mp >= (int)ctx->mps.size() || !pusher) return PTL_EHANDLE;
+    if (pusher->nforcings < 0 || pusher->nforcings > PTL_MAX_FORCINGS) return PTL_EINVAL;
+    const MultiPop& M = ctx->mps[mp];
+    bool has_cb = cb && (cb->nwalls > 0 || cb->count_collisions);
+    if (cb && (cb->nwalls < 0 || cb->nwalls > PTL_MAX_WALLS)) return PTL_EINVAL;
+    if (has_cb) {
+        for (int k = 0; k < cb->nwalls; k++) {
+            int pi = (cb->wall[k].species >= 0 && cb->wall[k].species < PTL_NSPECIES) ? M.by_species[cb->wall[k].species] : -1;
+            long long cap = pi >= 0 ? ctx->pops[pi].v.capacity : 1024;
+            if (cap > (1LL << 22)) cap = 1LL << 22;
+            int32_t rc = ensure_wall(ctx, k, cap); if (rc) return rc;
+        }
+    }
+    AdvanceParams A;
+    fill_params(ctx, &M, A);
+    A.pusher = *pusher;
+    if (has_cb) A.cb = *cb;
+    A.has_cb = has_cb ? 1 : 0;
+    A.tfinal = tfinal;
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    CK(cudaMemsetAsync(&ctx->d_sc->substeps, 0, 2 * sizeof(unsigned long long), ctx->stream));   // substeps, births
+    for (int pi : M.pops) ctx->pops[pi].iup = 0;   // advance_init!: iup = 1  (mixed_population.jl:101)
+    bool first = true;
+    for (;;) {
+        int32_t rc = sync_scalars(ctx); if (rc) return rc;     // read every popl.n (one host sync per pass)
+        long long total = 0;
+        for (int pi : M.pops) {
+            Pop& P = ctx->pops[pi];
+            long long n = (long long)ctx->h_sc->pop_n[P.slot];
+            if (n > P.v.capacity) {   // children beyond capacity were dropped and flagged by the kernel
+                n = P.v.capacity;
+                rc = set_n(ctx, P, n); if (rc) return rc;
+            }
+            long long rows = n - P.iup;
+            if (rows > 0) {
+                const Table& T = ctx->tables[P.table];
+                rc = launch_advance(ctx, P.v.species, A, P.iup, n, first, has_cb, T.smem_bytes);
+                if (rc) return rc;
+                total += rows;
+                ctx->stats.rows += rows;
+                P.iup = n;
+            }
+        }
+        ctx->stats.passes++;
+        first = false;
+        if (total == 0) break;     // advance1! returned 0 (mixed_population.jl:44-46)
+    }
+    ctx->step++;
+    ctx->stats.substeps = (int64_t)ctx->h_sc->substeps;
+    ctx->stats.births = (int64_t)ctx->h_sc->births;
+    return ctx->h_sc->flags;
+}
+
+EXPORT int32_t ptl_last_advance_stats(ptl_context* ctx, ptl_advance_stats* out) {
+    if (!ctx || !out) return PTL_EINVAL;
+    *out = ctx->stats;
+    return 0;
+}
+
+EXPORT int32_t ptl_collision_counts(ptl_context* ctx, int32_t table, int64_t* counts, int32_t clear) {
+    if (!ctx || table < 0 || table >= (int)ctx->tables.size() || !counts) return PTL_EHANDLE;
+    Table& T = ctx->tables[table];
+    size_t bytes = sizeof(unsigned long long) * (T.v.nprocs + 1);
+    CK(cudaMemcpyAsync(counts, T.d_counts, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clear) CK(cudaMemsetAsync(T.d_counts, 0, bytes, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+EXPORT int64_t ptl_wall_records(ptl_context* ctx, int32_t iwall, int64_t max_n, double* x3, double* p3, double* w, double* t, int32_t clear) {
+    if (!ctx || iwall < 0 || iwall >= PTL_MAX_WALLS) return PTL_EINVAL;
+    Wall& W = ctx->walls[iwall];
+    if (!W.block) return 0;
+    int32_t rc = sync_scalars(ctx); if (rc) return rc;
+    long long total = (long long)ctx->h_sc->wall_n[iwall];
+    if (total > W.b.capacity) total = W.b.capacity;
+    long long n = total < max_n ? total : max_n;
+    if (n > 0) {
+        rc = ensure_tmp(ctx, sizeof(double) * 3 * (size_t)n); if (rc) return rc;
+        for (int which = 0; which < 2; which++) {
+            double* dst = which == 0 ? x3 : p3;
+            if (!dst) continue;
+            int c0 = which * 3;
+            k_planar_to_aos3<<<grid_for(n, 256), 256, 0, ctx->stream>>>(W.b.col[c0], W.b.col[c0 + 1], W.b.col[c0 + 2], (double*)ctx->d_tmp, n);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(dst, ctx->d_tmp, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (w) CK(cudaMemcpyAsync(w, W.b.col[6], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (t) CK(cudaMemcpyAsync(t, W.b.col[7], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (clear) CK(cudaMemsetAsync(W.b.n, 0, sizeof(unsigned long long), ctx->stream));
+    return total;
+}
+
+// =====================================================================================================
+// test / diagnostic entry points
+// =====================================================================================================
+EXPORT int32_t ptl_collide_test(ptl_context* ctx, int32_t species, int32_t table, int32_t j, int64_t n, const double* p3, uint64_t uid0,
+                                double* out) {
+    if (!ctx || table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
+    const Table& T = ctx->tables[table];
+    if (j < 0 || j >= T.v.nprocs || species < 0 || species >= PTL_NSPECIES || n < 0) return PTL_EINVAL;
+    if (n == 0) return 0;
+    AdvanceParams A;
+    fill_params(ctx, nullptr, A);
+    int32_t rc = ensure_tmp(ctx, sizeof(double) * (size_t)n * 27); if (rc) return rc;
+    double* d_p = (double*)ctx->d_tmp;
+    double* d_o = d_p + 3 * n;
+    CK(cudaMemcpyAsync(d_p, p3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    DISPATCH_SPECIES(species, k_collide_test<SP><<<grid_for(n, 128), 128, 0, ctx->stream>>>(A, T.v, j, n, d_p, uid0, d_o));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_o, sizeof(double) * 24 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+namespace {
+__global__ void k_rng_test(unsigned long long uid, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, int n, double* out) {
+    Rng rng;
+    rng.init(uid, DOM_COLLISION);
+    for (int i = 0; i < n; i++) out[i] = rng.u(step, seed_lo, seed_hi);
+}
+}  // namespace
+
+EXPORT int32_t ptl_rng_test(ptl_context* ctx, uint64_t uid, uint64_t seed, uint32_t step, int32_t n, double* out) {
+    if (!ctx || n < 0 || !out) return PTL_EINVAL;
+    if (n == 0) return 0;
+    int32_t rc = ensure_tmp(ctx, sizeof(double) * n); if (rc) return rc;
+    k_rng_test<<<1, 1, 0, ctx->stream>>>(uid, step, (uint32_t)seed, (uint32_t)(seed >> 32), n, (double*)ctx->d_tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->d_tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

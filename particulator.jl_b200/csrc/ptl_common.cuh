@@ -1,0 +1,171 @@
+// ptl_common.cuh — device-side views, constants and the counter-based RNG shared by all kernels.
+//
+// Data layout in HBM: every population is a planar SoA of 10 double columns
+// (x0,x1,x2,p0,p1,p2,w,t,s,r), one uint8 `active` column and one uint64 `uid` column, each
+// `capacity` long and 256-byte aligned, so that a warp reading one column touches one
+// contiguous 256 B (double) span -> 100 % sector efficiency.  The particle count `n` of each
+// population lives in device memory (births append with atomicAdd).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/particulator_b200.h"
+
+namespace ptl {
+
+// ---- constants: reference src/constants.jl (CODATA-2014), same expression order ----------------
+constexpr double CO_C = 299792458.0;                  // constants.jl:37
+constexpr double CO_E = 1.6021766208e-19;             // constants.jl:50-54
+constexpr double CO_ME = 9.10938356e-31;              // constants.jl:52
+constexpr double CO_EPS0 = 8.854187817620389e-12;     // constants.jl:55
+constexpr double CO_ALPHA = 0.0072973525664;          // constants.jl:60
+constexpr double CO_HBAR = 1.0545718001391127e-34;    // constants.jl:77
+constexpr double CO_PI = 3.141592653589793;
+constexpr double CO_RE = (CO_E * CO_E) / (CO_ME * (CO_C * CO_C)) / (4 * CO_PI * CO_EPS0);  // :157
+constexpr double CO_A0 = CO_HBAR / (CO_ME * CO_C * CO_ALPHA);                               // :160
+constexpr double CO_MC2 = CO_ME * (CO_C * CO_C);                                            // :163
+constexpr double CO_C2 = CO_C * CO_C;
+constexpr double DBL_EPS = 2.220446049250313e-16;     // eps(Float64), mixed_population.jl:66
+
+constexpr int MAX_ORDER = 8;
+constexpr int MAX_SB = 8;
+constexpr int MAX_CHEBLOSS = 4;
+
+enum Column { COL_X0 = 0, COL_X1, COL_X2, COL_P0, COL_P1, COL_P2, COL_W, COL_T, COL_S, COL_R, COL_ACTIVE, COL_UID, NCOLS };
+
+struct PopView {
+    double* col[10];                 // x0,x1,x2,p0,p1,p2,w,t,s,r
+    uint8_t* active;
+    uint64_t* uid;
+    unsigned long long* n;           // device-resident particle count (population.jl:9)
+    long long capacity;
+    double energy_cut;
+    int species;
+    int present;
+};
+
+struct TableView {
+    int kind;                        // 0 = Chebyshev, 1 = linear
+    int nprocs;
+    int order, k;
+    double xmax;
+    const double* rate;              // cheb: [order, nprocs, k+1]; linear: [nprocs, nE]
+    const double* ratebound;         // cheb: [order, k+1]
+    int grid_kind, nE;
+    double L1, L2, maxrate;
+    const ptl_process_desc* procs;   // device copy
+    unsigned long long* counts;      // [nprocs + 1]
+};
+
+struct SbView {
+    int ncum, nE;
+    const double* log_energy;
+    const double* data;              // [ncum, nE], ncum fastest
+};
+
+struct ChebLossView {
+    int order, k;
+    double xmax;
+    const double* ec;
+    const double* pc;
+};
+
+struct WallBuf {
+    double* col[8];                  // x0,x1,x2,p0,p1,p2,w,t
+    unsigned long long* n;
+    long long capacity;
+};
+
+struct AdvanceParams {
+    PopView pop[PTL_NSPECIES];       // indexed by species (MultiPopulation index, mixed_population.jl:15)
+    TableView tab[PTL_NSPECIES];     // table of that species' population
+    SbView sb[MAX_SB];
+    ChebLossView cl[MAX_CHEBLOSS];
+    ptl_pusher_desc pusher;
+    ptl_callback_desc cb;
+    WallBuf wall[PTL_MAX_WALLS];
+    double tfinal;
+    uint32_t seed_lo, seed_hi, step;
+    int has_cb;
+    int* flags;                      // sticky PTL_ERR_* bits
+    unsigned long long* substeps;    // global sub-step counter
+    unsigned long long* births;
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11) -------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr uint32_t DOM_COLLISION = 0u;
+constexpr uint32_t DOM_CHILD_UID = 0x5EED0001u;
+constexpr uint32_t DOM_ROULETTE = 0x5EED0002u;
+constexpr uint32_t DOM_SPLIT = 0x5EED0003u;
+
+// 64 random bits -> double in the OPEN interval (0,1): (m + 0.5) * 2^-52 with m the top 52 bits.
+// Built as [1,2) mantissa + one exact add (no int->double conversion).
+__device__ __forceinline__ double bits_to_u01(uint32_t lo, uint32_t hi) {
+    uint32_t dhi = 0x3FF00000u | (hi >> 12);
+    uint32_t dlo = (hi << 20) | (lo >> 12);
+    return __hiloint2double((int)dhi, (int)dlo) + (-1.0 + 0x1.0p-53);
+}
+
+// Per-particle stream: replaces the task-local rand() of the reference (src/util.jl:17 and every
+// collide).  The n-th uniform of (uid, advance call) is word pair (n & 1) of block n >> 1.
+struct Rng {
+    uint32_t k0, k1;
+    uint32_t idx;
+    uint32_t cblock;
+    uint32_t c2, c3;
+
+    __device__ __forceinline__ void init(uint64_t uid, uint32_t domain) {
+        k0 = (uint32_t)uid;
+        k1 = (uint32_t)(uid >> 32) ^ domain;
+        idx = 0;
+        cblock = 0xFFFFFFFFu;
+        c2 = c3 = 0;
+    }
+    __device__ __forceinline__ double u(uint32_t step, uint32_t seed_lo, uint32_t seed_hi) {
+        uint32_t block = idx >> 1;
+        double r;
+        if (idx & 1) {
+            if (cblock != block) {
+                uint32_t o[4];
+                philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
+                c2 = o[2]; c3 = o[3]; cblock = block;
+            }
+            r = bits_to_u01(c2, c3);
+        } else {
+            uint32_t o[4];
+            philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
+            c2 = o[2]; c3 = o[3]; cblock = block;
+            r = bits_to_u01(o[0], o[1]);
+        }
+        idx++;
+        return r;
+    }
+    __device__ __forceinline__ void skip() { idx++; }
+};
+
+__device__ __forceinline__ void child_uids(uint64_t parent, uint32_t idx, uint32_t step, uint32_t seed_lo, uint32_t seed_hi,
+                                           uint64_t out[2]) {
+    uint32_t o[4];
+    philox4x32_10(idx, step, seed_lo, seed_hi, (uint32_t)parent, (uint32_t)(parent >> 32) ^ DOM_CHILD_UID, o);
+    out[0] = ((uint64_t)o[1] << 32) | o[0];
+    out[1] = ((uint64_t)o[3] << 32) | o[2];
+}
+
+}  // namespace ptl

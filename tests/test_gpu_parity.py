@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tiers:
+  * bit-exact: RNG stream, table lookups (Chebyshev and LinRange), droplow!/repack! permutation;
+  * deterministic replay: same Philox deviates through both codes, per-particle state matched by uid,
+    rel 1e-6 in fp64 (tolerance written below as REPLAY_RTOL);
+  * properties at larger sizes that do not need the oracle.
+Run on a B200 with:  python -m pytest tests -m gpu -x -q"""
+import numpy as np
+import pytest
+
+import particulator_b200 as P
+from conftest import make_world, default_pusher
+
+pytestmark = pytest.mark.gpu
+
+co = P.co
+REPLAY_RTOL = 1e-6     # north-star bound for the deterministic path in fp64
+EVENT_RTOL = 1e-9      # single collide() events (no error accumulation)
+DT = 2.5e-11
+
+
+# ---------------------------------------------------------------------------------------------------
+# bit-exact tier
+# ---------------------------------------------------------------------------------------------------
+def test_rng_stream_bit_exact(gctx, octx):
+    for uid, seed, step in [(1, 0, 0), (2 ** 40 + 17, 12345678901234567, 3), (2 ** 64 - 1, 2 ** 64 - 1, 2 ** 32 - 1)]:
+        a = gctx.rng_test(uid, seed, step, 257)
+        b = octx.rng_test(uid, seed, step, 257)
+        assert np.array_equal(a, b)
+        assert np.all((a > 0) & (a < 1))
+
+
+def _energies(xmax):
+    rng = np.random.default_rng(1)
+    e = np.exp(rng.uniform(np.log(1e-3 * co.eV), np.log(0.9999 * xmax), 200000))
+    edges = xmax * 2.0 ** np.arange(-40, 0)
+    edge_lo = np.nextafter(edges, 0)
+    edge_hi = np.nextafter(edges, np.inf)
+    return np.concatenate([e, edges, edge_lo, edge_hi, [0.0, 1e3 * co.eV, 1e2 * co.eV]])
+
+
+@pytest.mark.parametrize("name", ["electron", "photon", "positron"])
+def test_chebyshev_table_lookup_bit_exact(gctx, octx, air_tables, name):
+    tab = air_tables[name]
+    e = _energies(tab.b.xmax)
+    rg, bg = gctx.table_eval(tab, e)
+    ro, bo = octx.table_eval(tab, e)
+    assert np.array_equal(rg.view(np.uint64), ro.view(np.uint64))
+    assert np.array_equal(bg.view(np.uint64), bo.view(np.uint64))
+    assert gctx.error_flags(clear=True) == 0
+
+
+def test_linear_table_lookup(gctx, octx):
+    lin = P.synthetic_lxcat_table(grid_kind=0)
+    e = np.random.default_rng(2).uniform(0, 99.99, 100000) * co.eV
+    rg, bg = gctx.table_eval(lin, e)
+    ro, bo = octx.table_eval(lin, e)
+    assert np.array_equal(rg.view(np.uint64), ro.view(np.uint64))      # LinRange grid: bit-exact
+    assert np.array_equal(bg, bo)
+    loglin = P.synthetic_lxcat_table(grid_kind=1)
+    e = np.exp(np.random.default_rng(3).uniform(np.log(2e-3), np.log(99.0), 100000)) * co.eV
+    rg, _ = gctx.table_eval(loglin, e)
+    ro, _ = octx.table_eval(loglin, e)
+    # LogLinRange needs log/exp (util.jl:118-127): libm vs libdevice differ in the last ulp
+    np.testing.assert_allclose(rg, ro, rtol=1e-9, atol=1e-9 * loglin.maxrate)
+
+
+def _random_pop(rng, n, frac_dead):
+    x = rng.normal(size=(n, 3))
+    K = np.exp(rng.uniform(np.log(5e2), np.log(1e7), n)) * co.eV
+    pn = P.momentum_norm_from_kin(P.ELECTRON, K)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return dict(x=x, p=d * pn[:, None], w=rng.uniform(0.5, 2, n), t=rng.uniform(0, 1e-9, n), s=rng.uniform(0, 3, n),
+                r=rng.uniform(0, 1e12, n), active=(rng.random(n) >= frac_dead).astype(np.uint8),
+                uid=np.arange(1, n + 1, dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n,frac_dead", [(1, 0.0), (1, 1.0), (31, 0.5), (1024, 0.3), (1025, 0.9), (100003, 0.1), (100003, 0.999),
+                                          (5000, 0.0), (5000, 1.0), (262144, 0.5)])
+def test_droplow_repack_same_permutation(gctx, octx, air_tables, n, frac_dead):
+    rng = np.random.default_rng(n)
+    st = _random_pop(rng, n, frac_dead)
+    res = []
+    for ctx in (gctx, octx):
+        pop = P.Population(ctx, P.ELECTRON, n + 10, st, air_tables["electron"], 1e3 * co.eV)
+        n1 = P.repack(pop)
+        a = pop.download()
+        n2 = P.droplow(pop)
+        b = pop.download()
+        res.append((n1, a, n2, b))
+    (n1g, ag, n2g, bg), (n1o, ao, n2o, bo) = res
+    assert n1g == n1o == int(st["active"].sum())
+    assert n2g == n2o
+    for g, o in ((ag, ao), (bg, bo)):
+        for k in g:
+            assert np.array_equal(g[k], o[k]), k       # same rows in the same order, bit for bit
+
+
+def test_diagnostics_match_oracle(gctx, octx, air_tables):
+    st = _random_pop(np.random.default_rng(5), 77777, 0.2)
+    d = []
+    for ctx in (gctx, octx):
+        pop = P.Population(ctx, P.ELECTRON, 80000, st, air_tables["electron"], 1e3 * co.eV)
+        d.append((pop.diag(), P.meanenergy(pop), P.spread(pop), P.posvar(pop), P.maxenergy(pop), P.nactives(pop), P.weight(pop)))
+    (dg, meg, spg, pvg, mxg, nag, wg), (do, meo, spo, pvo, mxo, nao, wo) = d
+    assert nag == nao and dg.n == do.n
+    assert mxg == pytest.approx(mxo, rel=1e-14)     # kinenergy: FMA contraction on the device, none in the oracle
+    np.testing.assert_allclose([wg, meg], [wo, meo], rtol=1e-12)
+    np.testing.assert_allclose(spg[0], spo[0], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(spg[1], spo[1], rtol=1e-9)
+    np.testing.assert_allclose(pvg, pvo, rtol=1e-9)
+    hg = gctx and P.Population(gctx, P.ELECTRON, 80000, st, air_tables["electron"], 1e3 * co.eV).histogram("energy", 1e3 * co.eV, 1e7 * co.eV, 64, True)
+    ho = P.Population(octx, P.ELECTRON, 80000, st, air_tables["electron"], 1e3 * co.eV).histogram("energy", 1e3 * co.eV, 1e7 * co.eV, 64, True)
+    np.testing.assert_allclose(hg, ho, rtol=1e-9, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------------
+# deterministic replay: single collide() events, every process
+# ---------------------------------------------------------------------------------------------------
+def _momenta(species, n, lo_eV, hi_eV, seed):
+    rng = np.random.default_rng(seed)
+    K = np.exp(rng.uniform(np.log(lo_eV), np.log(hi_eV), n)) * co.eV
+    pn = P.momentum_norm_from_kin(species, K)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return d * pn[:, None]
+
+
+CASES = [("electron", P.ELECTRON, 1.1e3, 2e8), ("positron", P.POSITRON, 2.5e2, 2e8), ("photon", P.PHOTON, 1.1e3, 2e8)]
+
+
+@pytest.mark.parametrize("name,species,lo,hi", CASES)
+def test_collide_events_replay(gctx, octx, air_tables, name, species, lo, hi):
+    tab = air_tables[name]
+    gctx.set_rng(7, 3)
+    octx.set_rng(7, 3)
+    for j, proc in enumerate(tab.proc):
+        lo_j = lo
+        if proc.name == "BetheHeitler":
+            lo_j = 1.03e6          # above 2 mc^2
+        if proc.name == "RBEB":
+            lo_j = max(lo, 1.05 * proc.B / co.eV)
+        p3 = _momenta(species, 20000, lo_j, hi, 100 + j)
+        g = gctx.collide_test(species, tab, j, p3, uid0=1000)
+        o = octx.collide_test(species, tab, j, p3, uid0=1000)
+        same_flow = (g[:, 3] == o[:, 3]) & (g[:, 0] == o[:, 0])
+        # control-flow flips of a rejection test are possible only when a compare is within rounding of its
+        # threshold: allow at most 2 in 20000 events and require agreement everywhere else
+        assert (~same_flow).sum() <= 2, (proc.name, int((~same_flow).sum()))
+        assert np.array_equal(g[same_flow, :3], o[same_flow, :3]), proc.name
+        scale = np.linalg.norm(p3, axis=1)[same_flow, None]
+        for c0 in (4, 8, 12):
+            err = np.abs(g[same_flow, c0:c0 + 3] - o[same_flow, c0:c0 + 3]) / scale
+            assert err.max() <= EVENT_RTOL, (proc.name, c0, err.max())
+        np.testing.assert_allclose(g[same_flow][:, [7, 11, 15]], o[same_flow][:, [7, 11, 15]], rtol=1e-12, atol=0)
+    assert gctx.error_flags(clear=True) == 0 and octx.error_flags(clear=True) == 0
+
+
+def test_lxcat_collide_events_replay(gctx, octx):
+    tab = P.synthetic_lxcat_table()
+    gctx.set_rng(1, 1)
+    octx.set_rng(1, 1)
+    rng = np.random.default_rng(4)
+    v = rng.normal(size=(5000, 3)) * 1.5e6
+    for j, proc in enumerate(tab.proc):
+        g = gctx.collide_test(P.SLOW_ELECTRON, tab, j, v, uid0=5)
+        o = octx.collide_test(P.SLOW_ELECTRON, tab, j, v, uid0=5)
+        assert np.array_equal(g[:, :4], o[:, :4]), proc.name
+        np.testing.assert_allclose(g[:, 4:16], o[:, 4:16], rtol=1e-9, atol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# deterministic replay: full advance! steps, per-particle state matched by uid
+# ---------------------------------------------------------------------------------------------------
+def _by_uid(pop):
+    d = pop.download()
+    order = np.argsort(d["uid"], kind="stable")
+    return {k: v[order] for k, v in d.items()}
+
+
+def _compare_populations(gp, op, label, budget=0.002):
+    g, o = _by_uid(gp), _by_uid(op)
+    ug, uo = g["uid"], o["uid"]
+    common, ig, io = np.intersect1d(ug, uo, return_indices=True)
+    nmiss = (len(ug) - len(common)) + (len(uo) - len(common))
+    assert nmiss <= max(2, budget * max(len(ug), 1)), (label, len(ug), len(uo), len(common))
+    if len(common) == 0:
+        return 0
+    pscale = np.maximum(np.linalg.norm(o["p"][io], axis=1), 1e-300)[:, None]
+    bad = (np.abs(g["p"][ig] - o["p"][io]) / pscale).max(axis=1) > REPLAY_RTOL
+    bad |= (np.abs(g["x"][ig] - o["x"][io])).max(axis=1) > REPLAY_RTOL * np.maximum(np.abs(o["x"][io]).max(axis=1), co.c * DT)
+    bad |= np.abs(g["t"][ig] - o["t"][io]) > 1e-6 * DT
+    bad |= np.abs(g["s"][ig] - o["s"][io]) > REPLAY_RTOL * np.maximum(np.abs(o["s"][io]), 1.0)
+    bad |= np.abs(g["r"][ig] - o["r"][io]) > REPLAY_RTOL * np.maximum(np.abs(o["r"][io]), 1.0)
+    bad |= g["active"][ig] != o["active"][io]
+    bad |= g["w"][ig] != o["w"][io]
+    # a mismatching particle is one whose trajectory took a different branch at a compare within rounding of its
+    # threshold; the budget is deliberately tiny and the count is reported
+    assert bad.sum() <= max(2, budget * len(common)), (label, int(bad.sum()), len(common))
+    return int(bad.sum()) + nmiss
+
+
+@pytest.mark.parametrize("seed,n_e,n_g,n_p", [(0, 3000, 3000, 1000), (1, 257, 0, 0), (2, 0, 5000, 0), (3, 0, 0, 777)])
+def test_advance_replay_against_oracle(gctx, octx, air_tables, seed, n_e, n_g, n_p):
+    worlds = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(seed, 0)
+        worlds.append(make_world(ctx, air_tables, n_e, n_g, n_p, cap=40000, seed=seed))
+    psh = default_pusher()
+    t = 0.0
+    for step in range(2):
+        t += DT
+        for mp, *_ in worlds:
+            P.advance(mp, psh, t)
+        sg, so = P.last_advance_stats(worlds[0][0]), P.last_advance_stats(worlds[1][0])
+        assert abs(sg["substeps"] - so["substeps"]) <= 2e-3 * so["substeps"] + 50, (sg, so)
+        for k, label in ((1, "electron"), (2, "photon"), (3, "positron")):
+            _compare_populations(worlds[0][k], worlds[1][k], f"{label} step {step}")
+        for mp, *pops in worlds:
+            for q in pops:
+                P.droplow(q)
+        for k in (1, 2, 3):
+            assert abs(len(worlds[0][k]) - len(worlds[1][k])) <= 3
+
+
+def test_photon_free_flight_and_time(gctx, air_tables):
+    """Photons (kappa ~ 1e-4): x advances by c*dt along p, t == tfinal, p untouched for non-colliding ones."""
+    mp, el, ph, po = make_world(gctx, air_tables, 0, 200000, 0, cap=300000, seed=9)
+    before = ph.download()
+    P.advance(mp, default_pusher(), DT)
+    after = ph.download()
+    n = len(before["w"])
+    same = np.all(after["p"][:n] == before["p"], axis=1) & (after["active"][:n] == 1)
+    assert same.mean() > 0.97
+    d = before["p"][same] / np.linalg.norm(before["p"][same], axis=1)[:, None]
+    np.testing.assert_allclose(after["x"][:n][same], before["x"][same] + d * co.c * DT, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(after["t"][:n][after["active"][:n] == 1], DT, rtol=0, atol=2.3e-16)
+
+
+def test_wall_and_counter_callbacks(gctx, octx, air_tables):
+    res = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(11, 0)
+        mp, el, ph, po = make_world(ctx, air_tables, 2000, 2000, 0, cap=20000, seed=4, emin=1e5, emax=1e7)
+        wall_e = P.WallCallback(P.ELECTRON, 3, 0.001, drop=True)
+        wall_g = P.WallCallback(P.PHOTON, 3, 0.002, drop=False)
+        cc = P.CollisionCounter()
+        cb = P.CombinedCallback((wall_e, wall_g, cc))
+        P.advance(mp, default_pusher(), DT, cb)
+        res.append((wall_e.accum, wall_g.accum, dict(cc.d), P.nactives(el), P.nactives(ph)))
+    (weg, wgg, cg, nag, npg), (weo, wgo, co_, nao, npo) = res
+    assert len(weg["w"]) == len(weo["w"]) > 0
+    assert len(wgg["w"]) == len(wgo["w"]) > 0
+    assert nag == nao and npg == npo
+    for a, b in ((weg, weo), (wgg, wgo)):
+        ka, kb = np.lexsort(a["x"].T), np.lexsort(b["x"].T)
+        np.testing.assert_allclose(a["x"][ka], b["x"][kb], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(a["p"][ka], b["p"][kb], rtol=1e-6, atol=1e-30)
+    assert set(cg) == set(co_)
+    for k in cg:
+        assert abs(cg[k] - co_[k]) <= 2 + 2e-3 * co_[k], (k, cg[k], co_[k])
+
+
+def test_capacity_overflow_is_flagged(gctx, air_tables):
+    mp, el, ph, po = make_world(gctx, air_tables, 3000, 0, 0, cap=3005, seed=6, emin=1e6, emax=1e7)
+    rc = P.advance(mp, default_pusher(), DT, check=False)
+    assert rc & 1                      # PTL_ERR_CAPACITY_OVERFLOW  (population.jl:107)
+    assert len(el) <= 3005
+    assert gctx.error_flags(clear=True) & 1
+
+
+def test_slow_electron_replay(gctx, octx):
+    """Config 5: LXCat linear table, null-collision dominated, attachment deaths and ionisation births."""
+    tab = P.synthetic_lxcat_table()
+    n = 5000
+    rng = np.random.default_rng(8)
+    st = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * co.eV / co.electron_mass) * 1.2,
+              s=-np.log(1 - rng.random(n)), uid=np.arange(1, n + 1, dtype=np.uint64))
+    E = 100 * co.Td * co.nair
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -E]), None))
+    pops = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(3, 0)
+        pop = P.Population(ctx, P.SLOW_ELECTRON, 4 * n, st, tab, 0.0)
+        mp = P.MultiPopulation(("slow", pop))
+        t = 0.0
+        for _ in range(3):
+            t += 1e-12
+            P.advance(mp, psh, t)
+        pops.append((pop, P.last_advance_stats(mp)))
+    (pg, sg), (po_, so) = pops
+    assert abs(sg["substeps"] - so["substeps"]) <= 2e-3 * so["substeps"] + 20
+    g, o = _by_uid(pg), _by_uid(po_)
+    common, ig, io = np.intersect1d(g["uid"], o["uid"], return_indices=True)
+    assert len(common) >= 0.998 * max(len(g["uid"]), len(o["uid"]))
+    vs = np.maximum(np.linalg.norm(o["p"][io], axis=1), 1e3)[:, None]
+    bad = (np.abs(g["p"][ig] - o["p"][io]) / vs).max(axis=1) > REPLAY_RTOL
+    bad |= g["active"][ig] != o["active"][io]
+    assert bad.sum() <= max(2, 0.002 * len(common)), int(bad.sum())
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at larger sizes (no oracle)
+# ---------------------------------------------------------------------------------------------------
+def test_large_population_properties(gctx, air_tables):
+    n = 2_000_000
+    mp, el, ph, po = make_world(gctx, air_tables, n, 0, 0, cap=int(1.3 * n), seed=10, emin=1e4, emax=5e7)
+    w0 = P.weight(el)
+    P.advance(mp, default_pusher(), DT)
+    st = P.last_advance_stats(mp)
+    assert st["substeps"] > 30 * n                  # kappa > 30 in STP air at dt = 2.5e-11 s
+    d = el.download(("t", "active", "uid"))
+    # the loop stops when trem <= eps(Float64) = 2.2e-16 *seconds* (absolute, mixed_population.jl:66)
+    assert np.all(np.abs(d["t"][d["active"] == 1] - DT) <= 2.3e-16)
+    assert len(np.unique(d["uid"])) == len(d["uid"])           # uid-keyed streams never collide here
+    n_before = len(el)
+    for q in mp:
+        P.droplow(q)
+    n_after = len(el)
+    assert n_after <= n_before
+    assert P.nactives(el) == n_after                # repack!: every surviving row is active
+    assert P.weight(el) >= 0.99 * w0
+    # idempotence of repack!
+    a = el.download(("uid",))["uid"]
+    P.repack(el)
+    assert np.array_equal(a, el.download(("uid",))["uid"])
+    assert gctx.error_flags() == 0

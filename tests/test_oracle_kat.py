@@ -1,0 +1,559 @@
+"""Pins for the CPU oracle and the host-side table builders (run without a GPU).
+
+The reference has no tests or golden vectors (test/runtests.jl:4-6) and Julia cannot run here, so the
+oracle is pinned by ANALYTIC KNOWN ANSWERS of the physics the reference cites and by external data:
+  * Philox4x32-10 known-answer vectors of the Random123 distribution;
+  * closed-form cross-sections vs numerical integrals of the differential cross-sections the
+    samplers draw from (Klein-Nishina, Moller, RBEB, screened Rutherford, Heitler annihilation);
+  * sampler distributions vs those differential cross-sections (Kolmogorov-Smirnov);
+  * energy / momentum conservation of every collide();
+  * NIST XCOM photon cross-sections for N and O (public data, values quoted below);
+  * exact relativistic motion in a uniform field for the RK2 pusher;
+  * a literal pure-Python transcription of repack!'s loops for the compaction permutation;
+  * exponential attenuation for the null-collision time stepping."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+from scipy import integrate, stats
+
+import particulator_b200 as P
+from particulator_b200 import cheby, processes as pr, tables
+from oracle_backend import oracle_backend
+
+co = P.co
+MC2 = co.electron_mc2
+
+
+# ---------------------------------------------------------------------------------------------------
+# RNG
+# ---------------------------------------------------------------------------------------------------
+def _philox(ctr, key):
+    b = oracle_backend()
+    c = (ctypes.c_uint32 * 4)(*ctr)
+    k = (ctypes.c_uint32 * 2)(*key)
+    o = (ctypes.c_uint32 * 4)()
+    b.dll.ora_philox_test(c, k, o)
+    return [int(v) for v in o]
+
+
+def test_philox4x32_10_known_answers():
+    # Random123 kat_vectors: philox4x32 10
+    assert _philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert _philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert _philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_uniform_stream(octx):
+    u = octx.rng_test(42, 7, 0, 200000)
+    assert np.all((u > 0) & (u < 1))
+    assert stats.kstest(u, "uniform").pvalue > 1e-3
+    # stream = f(uid, seed, step): changing any of them changes the stream; same triple reproduces it
+    assert np.array_equal(u[:100], octx.rng_test(42, 7, 0, 100))
+    for other in (octx.rng_test(43, 7, 0, 100), octx.rng_test(42, 8, 0, 100), octx.rng_test(42, 7, 1, 100)):
+        assert not np.array_equal(u[:100], other)
+    # 52-bit mantissa + half offset: u * 2^53 is an odd integer
+    m = u[:1000] * 2.0 ** 53
+    assert np.all(m == np.round(m)) and np.all(np.round(m).astype(np.int64) % 2 == 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# table lookups
+# ---------------------------------------------------------------------------------------------------
+def test_chebyshev_lookup_matches_independent_numpy_evaluation(octx, air_tables):
+    for name in ("electron", "photon", "positron"):
+        tab = air_tables[name]
+        rng = np.random.default_rng(0)
+        e = np.exp(rng.uniform(np.log(1e-2 * co.eV), np.log(0.999 * tab.b.xmax), 20000))
+        rates, bound = octx.table_eval(tab, e)
+        for j in range(len(tab.proc)):
+            ref = cheby.chebeval(e, tab.b, tab.rate[:, j, :])
+            np.testing.assert_allclose(rates[j], ref, rtol=1e-13, atol=1e-3)
+        np.testing.assert_allclose(bound, cheby.chebeval(e, tab.b, tab.ratebound), rtol=1e-13)
+
+
+def test_precheb_interval_edges():
+    b = cheby.BinaryIntervals(32, 1e3 * co.eV * 2 ** 18)
+    # 1 keV sits exactly on an interval boundary (collision_table.jl:119-122)
+    i_lo, _ = cheby.precheb(np.nextafter(1e3 * co.eV, 0), b, 3)
+    i_hi, t = cheby.precheb(1e3 * co.eV, b, 3)
+    assert i_hi == i_lo + 1
+    assert t[1] == -1.0                      # left edge of its interval: xi = -1
+    for i in range(1, 33):
+        l, r = b.interval(i)
+        ii, tt = cheby.precheb(np.array([l, 0.5 * (l + r)]), b, 3)
+        assert list(ii) == [i, i]
+        np.testing.assert_allclose(tt[1], [-1.0, 0.0], atol=1e-15)
+
+
+def test_chebfit_reproduces_function_at_nodes_and_bounds_error():
+    b = cheby.BinaryIntervals(32, 1e3 * co.eV * 2 ** 18)
+    proc = pr.RelativisticCoulomb(7)
+    f = lambda e: co.nair * pr.speed(P.ELECTRON, e) * proc.totalcs(e)
+    a = cheby.chebfit(f, b, 3)
+    for i in (5, 14, 20, 31):
+        l, r = b.interval(i)
+        x = cheby.chebnodes(3, l, r)
+        np.testing.assert_allclose(cheby.chebeval(x, b, a), f(x), rtol=1e-12)
+    e = np.exp(np.linspace(np.log(1e3 * co.eV), np.log(2e8 * co.eV), 4000))
+    assert np.max(np.abs(cheby.chebeval(e, b, a) / f(e) - 1)) < 5e-3     # <= 3.5e-3
+
+
+def test_linear_lookup_matches_numpy_interp(octx):
+    lin = P.synthetic_lxcat_table(grid_kind=0)
+    e = np.random.default_rng(1).uniform(0, 99.9, 5000) * co.eV
+    rates, bound = octx.table_eval(lin, e)
+    grid = lin.energy()
+    for j in range(len(lin.proc)):
+        np.testing.assert_allclose(rates[j], np.interp(e, grid, lin.rate[j]), rtol=1e-10, atol=1e-6)
+    assert np.all(bound == lin.maxrate)
+    np.testing.assert_allclose(rates.sum(axis=0), lin.maxrate, rtol=1e-12)      # explicit null row fills up to maxrate
+    loglin = P.synthetic_lxcat_table(grid_kind=1)
+    e = np.exp(np.random.default_rng(2).uniform(np.log(2e-3), np.log(99.0), 5000)) * co.eV
+    rates, _ = octx.table_eval(loglin, e)
+    grid = loglin.energy()
+    for j in range(len(loglin.proc)):
+        np.testing.assert_allclose(rates[j], np.interp(e, grid, loglin.rate[j]), rtol=1e-8, atol=1e-6)
+
+
+def test_rate_bound_dominates_total_rate(air_tables):
+    """The bound must stay above the summed rates (collisions.jl:186 asserts it at run time)."""
+    for name in ("electron", "photon", "positron"):
+        tab = air_tables[name]
+        e = np.exp(np.linspace(np.log(1e2 * co.eV), np.log(0.99 * tab.b.xmax), 5000))
+        tot = sum(cheby.chebeval(e, tab.b, tab.rate[:, j, :]) for j in range(len(tab.proc)))
+        rb = cheby.chebeval(e, tab.b, tab.ratebound)
+        assert np.all(rb >= tot * (1 - 1e-12))
+
+
+def test_process_order_is_by_descending_max_rate(air_tables):
+    tab = air_tables["electron"]
+    names = [p.name for p in tab.proc]
+    assert names[:2] == ["RelativisticCoulomb", "RelativisticCoulomb"]      # Coulomb dominates (Appendix C)
+    assert names[-2:] == ["SeltzerBerger", "SeltzerBerger"]                   # bremsstrahlung ~0.3 % of events
+    e = np.array([1e3, 1e4, 1e5, 1e6, 7e6, 3e7]) * co.eV
+    tot = sum(cheby.chebeval(e, tab.b, tab.rate[:, j, :]) for j in range(len(tab.proc)))
+    kappa = tot * 2.5e-11
+    np.testing.assert_allclose(kappa, [416, 153, 60, 38, 41, 44], rtol=0.03)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cross-sections: closed forms vs numerical integrals of the differential cross-sections
+# ---------------------------------------------------------------------------------------------------
+def _kn_dsde(eps, k):
+    """Klein-Nishina dσ/dε per electron, ε = E'/E, k = E/mc²."""
+    t = (1 - eps) / (k * eps)                 # 1 - cosθ
+    sin2 = t * (2 - t)
+    return math.pi * co.r_e ** 2 / k * (1 / eps + eps) * (1 - eps * sin2 / (1 + eps ** 2))
+
+
+@pytest.mark.parametrize("E_eV", [1e4, 1e5, 1e6, 1e7])
+def test_klein_nishina_total_cs_is_integral_of_differential(E_eV):
+    k = E_eV * co.eV / MC2
+    num, _ = integrate.quad(_kn_dsde, 1 / (1 + 2 * k), 1, args=(k,), epsabs=0, epsrel=1e-10)
+    assert pr.KleinNishinaCompton(1).totalcs(E_eV * co.eV) == pytest.approx(num, rel=1e-8)
+
+
+def test_compton_fit_tends_to_klein_nishina_and_matches_xcom():
+    barn = 1e-28
+    for Z, xcom in ((7, {1e5: 3.403, 1e6: 1.479, 1e7: 0.3581}), (8, {1e5: 3.880, 1e6: 1.691, 1e7: 0.4093})):
+        for E, sig in xcom.items():          # NIST XCOM incoherent scattering, b/atom
+            assert pr.Compton(Z).totalcs(E * co.eV) / barn == pytest.approx(sig, rel=0.03)
+            if E >= 1e6:
+                assert pr.Compton(Z).totalcs(E * co.eV) == pytest.approx(pr.KleinNishinaCompton(Z).totalcs(E * co.eV), rel=0.02)
+
+
+def test_photoelectric_and_pair_cross_sections_match_xcom():
+    barn = 1e-28
+    # NIST XCOM photo-electric absorption, b/atom
+    for Z, xcom in ((7, {1e4: 82.41, 1e5: 4.347e-2}), (8, {1e4: 147.9, 1e5: 8.264e-2})):
+        for E, sig in xcom.items():
+            assert pr.PhotoElectric(Z).totalcs(E * co.eV) / barn == pytest.approx(sig, rel=0.08)
+    # NIST XCOM pair production (nuclear + electron field), b/atom
+    for Z, xcom in ((7, {5e6: 5.398e-2 + 2.298e-3, 1e7: 0.1045 + 8.188e-3}), (8, {5e6: 7.051e-2 + 2.626e-3, 1e7: 0.1363 + 9.357e-3})):
+        for E, sig in xcom.items():
+            assert pr.BetheHeitler(Z).totalcs(E * co.eV) / barn == pytest.approx(sig, rel=0.08)
+    assert pr.BetheHeitler(7).totalcs(1.0e6 * co.eV) == 0.0              # below 2 mc²
+
+
+def _moller_dsde(eps, gam):
+    beta2 = 1 - 1 / gam ** 2
+    return (2 * math.pi * co.r_e ** 2 / (beta2 * (gam - 1)) *
+            ((gam - 1) ** 2 / gam ** 2 + 1 / eps * (1 / eps - (2 * gam - 1) / gam ** 2)
+             + 1 / (1 - eps) * (1 / (1 - eps) - (2 * gam - 1) / gam ** 2)))
+
+
+@pytest.mark.parametrize("E_eV", [5e3, 1e5, 1e7])
+def test_moller_total_cs_is_integral_of_differential(E_eV):
+    tcut = 1e3 * co.eV
+    E = E_eV * co.eV
+    gam = 1 + E / MC2
+    num, _ = integrate.quad(_moller_dsde, tcut / E, 0.5, args=(gam,), epsabs=0, epsrel=1e-10)
+    assert pr.Moller(1, tcut).totalcs(E) == pytest.approx(num, rel=1e-8)
+    assert pr.Moller(1, tcut).totalcs(1.5 * tcut) == 0 or pr.Moller(1, tcut).totalcs(1.5 * tcut) >= 0
+
+
+@pytest.mark.parametrize("orb", [pr.N2_ORBITALS[0], pr.N2_ORBITALS[4], pr.O2_ORBITALS[5]])
+@pytest.mark.parametrize("T_eV", [1e3, 1e5, 1e7])
+def test_rbeb_total_cs_is_integral_of_differential(orb, T_eV):
+    T = T_eV * co.eV
+    num, _ = integrate.quad(lambda W: pr.rbeb_dsdw(W, T, orb.B, orb.U), 0, (T - orb.B) / 2, epsabs=0, epsrel=1e-10, limit=200)
+    assert orb.totalcs(T) == pytest.approx(orb.N * num, rel=1e-7)
+    assert orb.totalcs(0.5 * orb.B) == 0.0
+
+
+@pytest.mark.parametrize("E_eV", [1e3, 1e5, 1e7])
+def test_coulomb_total_cs_is_integral_of_differential(E_eV):
+    Z = 7
+    K = E_eV * co.eV + 1e-4 * co.eV
+    a = 1.3413 * Z ** (-1 / 3) * co.a_0
+    g = 1 + K / MC2
+    p = math.sqrt(K * (K + 2 * MC2)) / co.c
+    beta = p / (g * co.electron_mass * co.c)
+    alpha = co.hbar ** 2 / (4 * p ** 2 * a ** 2)
+    A = (Z * co.r_e / (2 * beta ** 2 * g)) ** 2
+    # dσ/dΩ = A (1 - β² x)/(x + α)², x = sin²(θ/2), dΩ = 4π dx
+    num, _ = integrate.quad(lambda x: 4 * math.pi * A * (1 - beta ** 2 * x) / (x + alpha) ** 2, 0, 1, epsabs=0, epsrel=1e-11,
+                            points=[alpha, 10 * alpha, 100 * alpha] if alpha < 1e-3 else None, limit=500)
+    assert pr.RelativisticCoulomb(Z).totalcs(E_eV * co.eV) == pytest.approx(num, rel=1e-6)
+
+
+def _anih_dsde(eps, gam):
+    return math.pi * co.r_e ** 2 / (gam - 1) / eps * (1 + 2 * gam / (gam + 1) ** 2 - eps - 1 / ((gam + 1) ** 2 * eps))
+
+
+@pytest.mark.parametrize("E_eV", [1e4, 1e6, 1e8])
+def test_annihilation_total_cs_is_integral_of_differential(E_eV):
+    E = E_eV * co.eV
+    gam = 1 + E / MC2
+    sq = math.sqrt((gam - 1) / (gam + 1))
+    num, _ = integrate.quad(_anih_dsde, (1 - sq) / 2, (1 + sq) / 2, args=(gam,), epsabs=0, epsrel=1e-10)
+    assert pr.PositronAnihilation(1).totalcs(E) == pytest.approx(num, rel=1e-8)
+
+
+def test_continuum_loss_against_bethe_magnitude():
+    """Collision stopping power of air for 1 MeV electrons is 1.66 MeV cm²/g (NIST ESTAR); the restricted
+    loss with Tcut = T/2 is the full collision loss."""
+    rho = 1.205e-3 * 1e3             # kg/m3
+    nel = co.nair * 14.4             # electrons per m3 of air (0.79*14 + 0.21*16)
+    cl = tables.ContinuumLoss(nel, 85.7 * co.eV, 0.5e6 * co.eV)
+    L = cl.energy_loss(P.ELECTRON, 1e6 * co.eV)
+    estar = 1.66e6 * co.eV * 1e-4 * 1e3 * (rho / 1e3)      # J/m
+    assert L == pytest.approx(estar, rel=0.05)
+    ccl = tables.ChebContinuumLoss.from_loss(tables.ContinuumLoss(nel, 85.7 * co.eV, 1e3 * co.eV), 1e8 * co.eV, 4)
+    e = np.exp(np.linspace(np.log(2.1e3 * co.eV), np.log(9e7 * co.eV), 200))
+    ref = tables.ContinuumLoss(nel, 85.7 * co.eV, 1e3 * co.eV).energy_loss(P.ELECTRON, e)
+    np.testing.assert_allclose(cheby.chebeval(e, ccl.bints, ccl.ec), ref, rtol=2e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# samplers (oracle collide) vs the differential cross-sections, and conservation laws
+# ---------------------------------------------------------------------------------------------------
+def _table_with(procs, species):
+    return tables.collision_table_from_processes([(co.nair, p) for p in procs], species, 0.0)
+
+
+def _along_z(species, E, n):
+    pn = P.momentum_norm_from_kin(species, E)
+    p = np.zeros((n, 3))
+    p[:, 2] = pn
+    p[:, 1] = 1e-6 * pn
+    return p
+
+
+def _ks(samples, pdf, lo, hi):
+    grid = np.linspace(lo, hi, 4001)
+    cdf = np.concatenate([[0], np.cumsum(0.5 * (pdf(grid[1:]) + pdf(grid[:-1])) * np.diff(grid))])
+    cdf /= cdf[-1]
+    return stats.kstest(samples, lambda x: np.interp(x, grid, cdf)).pvalue
+
+
+def test_compton_sampler_follows_klein_nishina_and_conserves(octx):
+    tab = _table_with([pr.Compton(7)], P.PHOTON)
+    E = 1e6 * co.eV
+    p0 = _along_z(P.PHOTON, E, 40000)
+    out = octx.collide_test(P.PHOTON, tab, 0, p0)
+    assert np.all(out[:, 0] == 2) and np.all(out[:, 1] == P.ELECTRON)
+    pg, pe = out[:, 4:7], out[:, 8:11]
+    np.testing.assert_allclose(pg + pe, p0, rtol=0, atol=1e-12 * np.linalg.norm(p0[0]))       # momentum
+    Eg = np.linalg.norm(pg, axis=1) * co.c
+    Ee = P.kinenergy(P.ELECTRON, pe)
+    np.testing.assert_allclose(Eg + Ee, E, rtol=1e-9)                                          # energy
+    k = E / MC2
+    assert _ks(Eg / E, lambda e: _kn_dsde(e, k), 1 / (1 + 2 * k), 1) > 1e-3
+    cost = (pg @ p0[0]) / (np.linalg.norm(pg, axis=1) * np.linalg.norm(p0[0]))
+    np.testing.assert_allclose(cost, 1 - (1 - Eg / E) / (k * Eg / E), atol=1e-9)              # Compton relation
+
+
+def test_moller_sampler_distribution(octx):
+    tcut = 1e3 * co.eV
+    tab = _table_with([pr.Moller(7, tcut)], P.ELECTRON)
+    E = 1e5 * co.eV
+    out = octx.collide_test(P.ELECTRON, tab, 0, _along_z(P.ELECTRON, E, 40000))
+    E2 = P.kinenergy(P.ELECTRON, out[:, 8:11])
+    E1 = P.kinenergy(P.ELECTRON, out[:, 4:7])
+    np.testing.assert_allclose(E1 + E2, E, rtol=1e-9)
+    gam = 1 + E / MC2
+    assert _ks(E2 / E, lambda e: _moller_dsde(e, gam), tcut / E, 0.5) > 1e-3
+
+
+@pytest.mark.parametrize("T_eV", [3e3, 1e6])
+def test_rbeb_sampler_distribution_and_kinematics(octx, T_eV):
+    orb = pr.N2_ORBITALS[4]
+    tab = _table_with([orb], P.ELECTRON)
+    T = T_eV * co.eV
+    p0 = _along_z(P.ELECTRON, T, 40000)
+    out = octx.collide_test(P.ELECTRON, tab, 0, p0)
+    E1 = P.kinenergy(P.ELECTRON, out[:, 4:7])
+    E2 = P.kinenergy(P.ELECTRON, out[:, 8:11])
+    np.testing.assert_allclose(E1 + E2 + orb.B, T, rtol=1e-9)                                  # rbeb.jl:60-61
+    assert np.all(E2 < E1)
+    assert _ks(E2, lambda W: pr.rbeb_dsdw(W, T, orb.B, orb.U), 0, (T - orb.B) / 2) > 1e-3
+    # Lehtinen angles: cosθ_i = sqrt(E_i (E0 + 2mc²) / (E0 (E_i + 2mc²)))
+    c1 = (out[:, 4:7] @ p0[0]) / (np.linalg.norm(out[:, 4:7], axis=1) * np.linalg.norm(p0[0]))
+    np.testing.assert_allclose(c1, np.sqrt(E1 * (T + 2 * MC2) / (T * (E1 + 2 * MC2))), atol=1e-9)
+    # mean secondary energy is a few tens of eV
+    assert 10 * co.eV < np.median(E2) < 40 * co.eV if T_eV > 1e4 else True
+
+
+@pytest.mark.parametrize("E_eV", [1e4, 1e6])
+def test_coulomb_sampler_distribution_preserves_energy(octx, E_eV):
+    Z = 7
+    tab = _table_with([pr.RelativisticCoulomb(Z)], P.ELECTRON)
+    E = E_eV * co.eV
+    p0 = _along_z(P.ELECTRON, E, 60000)
+    out = octx.collide_test(P.ELECTRON, tab, 0, p0)
+    assert np.all(out[:, 0] == 1)
+    p1 = out[:, 4:7]
+    np.testing.assert_allclose(np.linalg.norm(p1, axis=1), np.linalg.norm(p0[0]), rtol=1e-12)  # elastic
+    cost = (p1 @ p0[0]) / np.linalg.norm(p0[0]) ** 2
+    x = (1 - cost) / 2
+    pn = np.linalg.norm(p0[0])
+    a = 1.3413 * Z ** (-1 / 3) * co.a_0
+    alpha = co.hbar ** 2 / (4 * pn ** 2 * a ** 2)
+    g = 1 + E / MC2
+    beta2 = 1 - 1 / g ** 2
+    # analytic CDF of (1 - β²x)/(x+α)² on [0,1]
+    F = lambda x: (1 + alpha * beta2) * (1 / alpha - 1 / (x + alpha)) - beta2 * np.log((x + alpha) / alpha)
+    assert stats.kstest(x, lambda q: F(np.clip(q, 0, 1)) / F(1.0)).pvalue > 1e-3
+
+
+def test_annihilation_sampler_and_conservation(octx):
+    tab = _table_with([pr.PositronAnihilation(7)], P.POSITRON)
+    E = 2e6 * co.eV
+    p0 = _along_z(P.POSITRON, E, 40000)
+    out = octx.collide_test(P.POSITRON, tab, 0, p0)
+    assert np.all(out[:, 0] == 5) and np.all(out[:, 1] == P.PHOTON) and np.all(out[:, 2] == P.PHOTON)
+    pa, pb = out[:, 8:11], out[:, 12:15]
+    np.testing.assert_allclose(pa + pb, p0, rtol=0, atol=1e-12 * np.linalg.norm(p0[0]))
+    Ea, Eb = np.linalg.norm(pa, axis=1) * co.c, np.linalg.norm(pb, axis=1) * co.c
+    np.testing.assert_allclose(Ea + Eb, E + 2 * MC2, rtol=1e-9)                                # energy incl. rest masses
+    gam = 1 + E / MC2
+    sq = math.sqrt((gam - 1) / (gam + 1))
+    assert _ks(Ea / (E + 2 * MC2), lambda e: _anih_dsde(e, gam), (1 - sq) / 2, (1 + sq) / 2) > 1e-3
+
+
+def test_seltzer_bethe_heitler_photoelectric_bhaba_conservation(octx, air_tables):
+    et, gt, pt = air_tables["electron"], air_tables["photon"], air_tables["positron"]
+    names = lambda t: [p.name for p in t.proc]
+    # bremsstrahlung: p_e + p_gamma = p0, k < T
+    j = names(et).index("SeltzerBerger")
+    E = 5e6 * co.eV
+    p0 = _along_z(P.ELECTRON, E, 20000)
+    out = octx.collide_test(P.ELECTRON, et, j, p0)
+    assert np.all(out[:, 0] == 2) and np.all(out[:, 1] == P.PHOTON)
+    np.testing.assert_allclose(out[:, 4:7] + out[:, 8:11], p0, atol=1e-12 * np.linalg.norm(p0[0]))
+    k = np.linalg.norm(out[:, 8:11], axis=1) * co.c
+    assert np.all(k < E) and np.all(k >= 0.99 * 100 * co.eV)              # gamma_min = 100 eV (seltzer.jl:26)
+    # pair production: kinetic energies sum to E - 2 mc²
+    j = names(gt).index("BetheHeitler")
+    E = 2e7 * co.eV
+    out = octx.collide_test(P.PHOTON, gt, j, _along_z(P.PHOTON, E, 20000))
+    assert np.all(out[:, 0] == 5) and np.all(out[:, 1] == P.ELECTRON) and np.all(out[:, 2] == P.POSITRON)
+    Ee, Ep = P.kinenergy(P.ELECTRON, out[:, 8:11]), P.kinenergy(P.POSITRON, out[:, 12:15])
+    np.testing.assert_allclose(Ee + Ep, E - 2 * MC2, rtol=1e-9)
+    assert abs(np.mean(Ee > Ep) - 0.5) < 0.02                              # rand(Bool) assignment is symmetric
+    # photo-electric: E_e = E_gamma - K-shell binding (403 eV for N)
+    j = names(gt).index("PhotoElectric")
+    E = 5e3 * co.eV
+    out = octx.collide_test(P.PHOTON, gt, j, _along_z(P.PHOTON, E, 5000))
+    assert np.all(out[:, 0] == 4) and np.all(out[:, 1] == P.ELECTRON)
+    Z = int(gt.proc[j].Z)
+    np.testing.assert_allclose(P.kinenergy(P.ELECTRON, out[:, 8:11]), E - pr.binding_energies(Z)[0], rtol=1e-9)
+    # Bhabha: E1 + E2 = E0, secondary above tcut
+    j = names(pt).index("Bhaba")
+    E = 1e6 * co.eV
+    out = octx.collide_test(P.POSITRON, pt, j, _along_z(P.POSITRON, E, 20000))
+    E1, E2 = P.kinenergy(P.POSITRON, out[:, 4:7]), P.kinenergy(P.ELECTRON, out[:, 8:11])
+    np.testing.assert_allclose(E1 + E2, E, rtol=1e-9)
+    assert np.all(E2 >= 0.999 * 1e2 * co.eV)
+    assert octx.error_flags() == 0
+
+
+def test_every_outgoing_state_draws_one_s(octx, air_tables):
+    """A.6: each state built with the 4-arg constructor consumes exactly one uniform for s = -log(u)."""
+    et = air_tables["electron"]
+    out = octx.collide_test(P.ELECTRON, et, 0, _along_z(P.ELECTRON, 1e6 * co.eV, 2000), uid0=77)
+    u = np.array([octx.rng_test(77 + i, 0, 0, int(out[i, 3])) for i in range(50)], dtype=object)
+    for i in range(50):
+        assert out[i, 7] == -math.log(u[i][-1])       # Coulomb: last draw is the new s of the scattered lepton
+        assert out[i, 3] >= 4 and (int(out[i, 3]) - 2) % 2 == 0      # phi, k x (u, z), s
+
+
+# ---------------------------------------------------------------------------------------------------
+# pusher, store, time stepping
+# ---------------------------------------------------------------------------------------------------
+def _single_species_world(ctx, species, tab, st, cut, cap=None):
+    pop = P.Population(ctx, species, cap or 4 * len(st["x"]) + 16, st, tab, cut)
+    return P.MultiPopulation(("p", pop)), pop
+
+
+def test_rk2_pusher_against_exact_relativistic_motion(octx):
+    """Uniform E along z, no collisions (empty table): p(t) = p0 + qEt exactly, z(t) from the hyperbolic motion."""
+    empty = tables.collision_table_from_processes([], P.ELECTRON, 0.0)
+    E0 = 5e5
+    n = 64
+    rng = np.random.default_rng(0)
+    K = np.exp(rng.uniform(np.log(1e3), np.log(1e7), n)) * co.eV
+    pn = P.momentum_norm_from_kin(P.ELECTRON, K)
+    p0 = np.zeros((n, 3)); p0[:, 2] = pn
+    st = dict(x=np.zeros((n, 3)), p=p0, s=np.ones(n))
+    mp, pop = _single_species_world(octx, P.ELECTRON, empty, st, 0.0)
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0, 0, -E0]), P.HomogeneousField([0, 0, 0])))
+    T, nsteps = 1e-9, 40
+    for k in range(nsteps):
+        P.advance(mp, psh, (k + 1) * T / nsteps)
+    d = pop.download()
+    F = co.elementary_charge * E0                       # force on an electron is +z for E = -E0 z
+    p_exact = pn + F * T
+    np.testing.assert_allclose(d["p"][:, 2], p_exact, rtol=1e-12)
+    en = lambda p: np.sqrt(MC2 ** 2 + (co.c * p) ** 2)
+    z_exact = (en(p_exact) - en(pn)) / F                # dz = dE/F
+    np.testing.assert_allclose(d["x"][:, 2], z_exact, rtol=1e-6)
+    np.testing.assert_allclose(d["t"], T, rtol=1e-12)
+
+
+def test_magnetic_field_rotates_momentum_and_keeps_energy(octx):
+    empty = tables.collision_table_from_processes([], P.ELECTRON, 0.0)
+    pn = P.momentum_norm_from_kin(P.ELECTRON, 1e6 * co.eV)
+    st = dict(x=np.zeros((1, 3)), p=np.array([[pn, 0.0, 0.0]]), s=np.ones(1))
+    mp, pop = _single_species_world(octx, P.ELECTRON, empty, st, 0.0)
+    B = 0.01
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0, 0, 0]), P.HomogeneousField([0, 0, B])))
+    gam = 1 + 1e6 * co.eV / MC2
+    omega = co.elementary_charge * B / (gam * co.electron_mass)
+    T = 0.25 * 2 * math.pi / omega
+    nsteps = 2000
+    for k in range(nsteps):
+        P.advance(mp, psh, (k + 1) * T / nsteps)
+    d = pop.download()
+    assert np.linalg.norm(d["p"][0]) == pytest.approx(pn, rel=1e-6)
+    # electron (q<0) in +z B: quarter turn from +x to +y
+    np.testing.assert_allclose(d["p"][0] / pn, [0.0, 1.0, 0.0], atol=1e-5)
+
+
+def _py_repack(active):
+    """Literal transcription of repack! (population.jl:229-259) on a list of row ids."""
+    rows = list(range(len(active)))
+    act = list(active)
+    l = len(rows)
+    if l == 0:
+        return []
+    while l > 0 and not act[l - 1]:
+        l -= 1
+    if l == 0:
+        return []
+    i = 1
+    while i <= l:
+        if not act[i - 1]:
+            rows[i - 1] = rows[l - 1]
+            act[i - 1] = act[l - 1]
+            l -= 1
+            while not act[l - 1]:
+                l -= 1
+        i += 1
+    return rows[:l]
+
+
+@pytest.mark.parametrize("n,frac", [(1, 0.0), (1, 1.0), (2, 0.5), (37, 0.3), (500, 0.9), (1000, 0.5), (1000, 0.0), (64, 1.0)])
+def test_oracle_repack_is_the_reference_permutation(octx, air_tables, n, frac):
+    rng = np.random.default_rng(n + int(100 * frac))
+    active = (rng.random(n) >= frac).astype(np.uint8)
+    pn = P.momentum_norm_from_kin(P.ELECTRON, 1e5 * co.eV)
+    st = dict(x=np.arange(3 * n, dtype=np.float64).reshape(n, 3), p=np.tile([0, 0, pn], (n, 1)), s=np.ones(n), active=active,
+              uid=np.arange(100, 100 + n, dtype=np.uint64))
+    pop = P.Population(octx, P.ELECTRON, n + 4, st, air_tables["electron"], 1e3 * co.eV)
+    new_n = P.repack(pop)
+    expect = _py_repack(active)
+    assert new_n == len(expect) == int(active.sum())
+    d = pop.download()
+    assert list(d["uid"]) == [100 + r for r in expect]
+    assert np.all(d["active"] == 1)
+    np.testing.assert_array_equal(d["x"][:, 0], [3.0 * r for r in expect])
+
+
+def test_droplow_uses_strict_less_and_birth_uses_less_equal(octx, air_tables):
+    cut = 1e3 * co.eV
+    pn_at = lambda E: P.momentum_norm_from_kin(P.ELECTRON, E)
+    E = np.array([0.5e3, 1e3, 2e3]) * co.eV
+    p = np.zeros((3, 3)); p[:, 2] = pn_at(E)
+    pop = P.Population(octx, P.ELECTRON, 16, dict(x=np.zeros((3, 3)), p=p, s=np.ones(3)), air_tables["electron"], cut)
+    Ek = P.kinenergy(P.ELECTRON, p)
+    assert P.droplow(pop) == int(np.sum(~(Ek < cut)))            # population.jl:278
+    j = P.add_particle(pop, [0, 0, 0], [0, 0, pn_at(0.9e3 * co.eV)], s=1.0)
+    assert j == -1                                                # population.jl:105
+    assert P.add_particle(pop, [0, 0, 0], [0, 0, pn_at(5e3 * co.eV)], s=1.0) == len(pop) - 1
+
+
+def test_photon_attenuation_is_exponential(octx, air_tables):
+    """Null-collision stepping: the fraction of 50 keV photons that has not interacted after time T is
+    exp(-nu T) with nu the summed tabulated rate."""
+    gt = air_tables["photon"]
+    E = 5e4 * co.eV
+    n = 100000
+    st = dict(x=np.zeros((n, 3)), p=_along_z(P.PHOTON, E, n), s=-np.log(1 - np.random.default_rng(3).random(n)))
+    mp, pop = _single_species_world(octx, P.PHOTON, gt, st, 1e3 * co.eV)
+    e_pop = P.Population(octx, P.ELECTRON, 4 * n, None, air_tables["electron"], 1e3 * co.eV)
+    mp = P.MultiPopulation(("photon", pop), ("electron", e_pop))
+    nu = sum(cheby.chebeval(np.array([E]), gt.b, gt.rate[:, j, :])[0] for j in range(len(gt.proc)))
+    T = 0.5 / nu
+    for k in range(4):
+        P.advance(mp, P.NullPusher(), (k + 1) * T / 4)
+    d = pop.download()
+    untouched = np.all(d["p"][:n] == st["p"], axis=1) & (d["active"][:n] == 1)
+    assert untouched.mean() == pytest.approx(math.exp(-0.5), abs=4 * math.sqrt(0.6 * 0.4 / n))
+    np.testing.assert_allclose(d["t"][:n][untouched], T, rtol=1e-12)
+
+
+def test_advance_births_inherit_time_and_position(octx, air_tables):
+    mp_world = __import__("conftest").make_world(octx, air_tables, 500, 0, 0, cap=8000, seed=1, emin=1e6, emax=1e7)
+    mp, el, ph, po = mp_world
+    octx.set_rng(5, 0)
+    P.advance(mp, __import__("conftest").default_pusher(), 2.5e-11)
+    st = P.last_advance_stats(mp)
+    assert st["passes"] >= 2 and st["births"] > 0
+    d = el.download()
+    act = d["active"] == 1
+    assert np.all(np.abs(d["t"][act] - 2.5e-11) <= 2.3e-16)       # eps(Float64) seconds, mixed_population.jl:66
+    assert len(np.unique(d["uid"])) == len(d["uid"])
+    born = d["uid"] > np.uint64(10 ** 9)
+    assert born.sum() == len(d["uid"]) - 500
+    assert octx.error_flags() == 0
+
+
+def test_rng_step_makes_results_reproducible(octx, air_tables):
+    from conftest import make_world, default_pusher
+    res = []
+    for _ in range(2):
+        ctx = __import__("oracle_backend").oracle_context()
+        ctx.set_rng(9, 4)
+        mp, el, ph, po = make_world(ctx, air_tables, 300, 300, 50, cap=6000, seed=2)
+        P.advance(mp, default_pusher(), 2.5e-11)
+        d = el.download()
+        o = np.argsort(d["uid"])
+        res.append({k: v[o] for k, v in d.items()})
+        assert ctx.get_rng() == (9, 5)
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
