@@ -1024,6 +1024,9 @@ static void do_one_collision(ora_context* ctx, const multipop_t* mp, pop_t* P, c
     pre_t pre;
     presample(T, eng, &pre);                /* :153 */
     if (pre.oob) FLAG(ctx, PTL_ERR_ENERGY_OUT_OF_TABLE);
+    /* stream layout: every collision test starts on an even draw index, so that the two halves of a Philox
+     * block are consumed pairwise in the same order by every particle (keeps the device lanes convergent) */
+    g->idx += g->idx & 1u;
     double xi = rng_u(g) * st->r;           /* :154 */
     outcome_t out;
     for (int j = 0; j < T->nprocs; j++) {   /* :166-180, unrolled in the reference */

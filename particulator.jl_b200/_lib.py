@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libparticulator_b200.so")
+LIB_PATH = os.environ.get("PTL_LIB_PATH") or os.path.join(_HERE, "csrc", "libparticulator_b200.so")   # env override: A/B builds of the same CUDA library
 
 MAX_PROCS = 32
 PROC_NPAR = 6

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
                 if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {   // :148-151
                     Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
                     if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+                    rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
                     double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;                     // :154
                     int jsel = -1;
                     const int np = T.nprocs;
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
                     switch (o.kind) {
                     case OUT_NULL:
                         r = setr<SP>(P, S, p);
-                        s = -log(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                        s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
                         break;
                     case OUT_STATE_CHANGE:
                         p = o.p1; s = o.s1; r = setr<SP>(P, S, p);

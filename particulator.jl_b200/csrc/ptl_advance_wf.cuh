@@ -1,0 +1,494 @@
+// ptl_advance_wf.cuh — K1 "wavefront" variant of the fused advance kernel for collision-dominated
+// species (electrons, positrons, slow electrons: kappa >> 1 sub-steps per particle per dt).
+//
+// Why: with one particle per thread and the reference's control flow (mixed_population.jl:61-88,
+// collisions.jl:142-199) a warp executes the UNION of what its 32 lanes do — push, 15-way process
+// switch, rejection loops with ~27 % acceptance (RBEB) — and ncu measured 6.6 active lanes per
+// instruction (profiles/r1_v1_electron_ncu_summary.csv).  Here a persistent CTA keeps the state of
+// WF_THREADS particles in SHARED MEMORY and splits the per-particle loop into short work units
+//     STEP (push to next event + null-collision selection) | COULOMB (sample + apply) |
+//     RBEB (rejection trials) | IONFIN (two-body kinematics + apply + birth) | OTHER (rare processes)
+// Every round the CTA counting-sorts its slots by pending unit (warp ballots + a shared-memory
+// prefix), so thread k executes the k-th unit of the sorted order and warps are coherent; finished
+// slots are refilled from a global row counter (dynamic load balance, no tail inside the block).
+// The arithmetic, the draw order and the per-particle Philox stream are exactly those of the
+// one-thread-per-particle kernel, so results are identical particle by particle.
+#pragma once
+#include "ptl_advance.cuh"
+
+namespace ptl {
+
+constexpr int WF_THREADS = 256;
+constexpr int WF_WARPS = WF_THREADS / 32;
+#ifndef WF_MIN_BLOCKS
+#define WF_MIN_BLOCKS 2
+#endif
+
+enum { WS_LOAD = 0, WS_STEP, WS_COULOMB, WS_RBEB, WS_IONFIN, WS_OTHER, WS_IDLE, WS_NCLASS };
+static_assert(WS_IDLE == 6 && WF_WARPS == 8, "the lane-parallel scheduler assumes 6 work classes x 8 warps");
+constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
+constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
+
+// double columns of the shared-memory particle pool
+enum { WD_X0 = 0, WD_X1, WD_X2, WD_P0, WD_P1, WD_P2, WD_T, WD_S, WD_R, WD_TREM, WD_ENG, WD_SCR, WD_NCOL };
+
+struct WfPool {
+    double* d;              // [WD_NCOL][WF_THREADS]
+    unsigned long long* uid;
+    long long* row;
+    uint32_t *idx, *cblock, *c2, *c3, *state;   // state: class | flags | (proc index << 16)
+    unsigned short* order;
+    uint32_t* cnt;          // [class][WF_WARPS], 64 entries
+};
+
+// doubles + uid/row + 5 u32 arrays + class-count matrix (64 entries) + order (u16), rounded up to 16 bytes
+constexpr size_t WF_POOL_BYTES =
+    ((sizeof(double) * WD_NCOL * WF_THREADS + 16 * WF_THREADS + 4 * 5 * WF_THREADS + 4 * 64 + 2 * WF_THREADS) + 15) / 16 * 16;
+__host__ __device__ inline size_t wf_pool_bytes() { return WF_POOL_BYTES; }
+
+__device__ __forceinline__ void wf_load_rng(const WfPool& S, int it, Rng& rng) {
+    unsigned long long uid = S.uid[it];
+    rng.k0 = (uint32_t)uid;
+    rng.k1 = (uint32_t)(uid >> 32) ^ DOM_COLLISION;
+    rng.idx = S.idx[it]; rng.cblock = S.cblock[it]; rng.c2 = S.c2[it]; rng.c3 = S.c3[it];
+}
+__device__ __forceinline__ void wf_store_rng(const WfPool& S, int it, const Rng& rng) {
+    S.idx[it] = rng.idx; S.cblock[it] = rng.cblock; S.c2[it] = rng.c2; S.c3[it] = rng.c3;
+}
+__device__ __forceinline__ Vec3 wf_get3(const WfPool& S, int c0, int it) {
+    return {S.d[(c0 + 0) * WF_THREADS + it], S.d[(c0 + 1) * WF_THREADS + it], S.d[(c0 + 2) * WF_THREADS + it]};
+}
+__device__ __forceinline__ void wf_put3(const WfPool& S, int c0, int it, Vec3 v) {
+    S.d[(c0 + 0) * WF_THREADS + it] = v.x; S.d[(c0 + 1) * WF_THREADS + it] = v.y; S.d[(c0 + 2) * WF_THREADS + it] = v.z;
+}
+#define WFD(col, it) S.d[(col) * WF_THREADS + (it)]
+
+// after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP
+template <int SP>
+__device__ __forceinline__ void wf_after_collision(const AdvanceParams& P, const SmemTable& T, const WfPool& S, int it, Vec3 p, double s) {
+    wf_put3(S, WD_P0, it, p);
+    WFD(WD_S, it) = s;
+    WFD(WD_R, it) = setr<SP>(P, T, p);
+    S.state[it] = WS_STEP | WF_VALID;
+}
+
+// process selection of do_one_collision! (collisions.jl:154-196).  The reference scans the processes
+// sequentially (xi -= nu_j until nu_j > xi); in exact arithmetic that picks the first j whose running sum
+// cum_j exceeds xi0 = u*r.  Lanes stop at different j (and null events scan all of them), so the scan is the
+// most divergent part of a STEP unit.  Here every lane evaluates all cum_j rows (uniform trip count, full
+// lanes) and takes the first j with cum_j > xi0; whenever some |cum_j - xi0| is within a guard band that is
+// orders of magnitude wider than the rounding differences between the two formulations, the lane falls back
+// to the reference's sequential scan on the per-process table, so the selected process is always identical.
+template <int TK, bool FAST>
+__device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, const Pre& pre,
+                                         double xi0, double r, bool& rate_bound_violated) {
+    const int np = T.nprocs;
+    int jsel = -1;
+    bool nearb = false;
+    const double guard = 1e-9 * r;
+    if (TK == 0 && FAST) {
+        // shared-memory layout [interval][m][16] (order 3, <= 16 processes, padded with -inf): two processes per LDS.128
+        const double2* c0 = reinterpret_cast<const double2*>(cum + 48 * pre.i);
+#pragma unroll
+        for (int j2 = 0; j2 < 8; j2++) {
+            if (2 * j2 >= np) break;
+            double2 a0 = c0[j2], a1 = c0[8 + j2], a2 = c0[16 + j2];
+            double d0 = fma(a2.x, pre.b, fma(a1.x, pre.a, a0.x)) - xi0;
+            double d1 = fma(a2.y, pre.b, fma(a1.y, pre.a, a0.y)) - xi0;
+            nearb |= (fabs(d0) < guard) | (fabs(d1) < guard);
+            jsel = (jsel < 0 && d0 > 0) ? 2 * j2 : jsel;
+            jsel = (jsel < 0 && d1 > 0) ? 2 * j2 + 1 : jsel;
+        }
+    } else if (TK == 0) {
+        const double* c = cum + T.order * np * pre.i;
+        for (int j = 0; j < np; j++) {
+            const double* a = c + T.order * j;
+            double cj = a[0];
+            if (T.order > 1) cj = fma(a[1], pre.a, cj);
+            if (T.order > 2) cj = fma(a[2], pre.b, cj);
+            if (T.order > 3) {
+                double tm2 = pre.a, tm1 = pre.b;
+                for (int m = 3; m < T.order; m++) {
+                    double tm = 2 * pre.a * tm1 - tm2;
+                    cj = fma(a[m], tm, cj);
+                    tm2 = tm1; tm1 = tm;
+                }
+            }
+            double d = cj - xi0;
+            nearb |= fabs(d) < guard;
+            if (jsel < 0 && d > 0) jsel = j;
+        }
+    } else {
+        for (int j = 0; j < np; j++) {
+            double c0 = __ldg(cum + j + (size_t)np * pre.i), c1 = __ldg(cum + j + (size_t)np * (pre.i + 1));
+            double d = (pre.a * c0 + (1 - pre.a) * c1) - xi0;
+            nearb |= fabs(d) < guard;
+            if (jsel < 0 && d > 0) jsel = j;
+        }
+    }
+    rate_bound_violated = false;
+    if (nearb) {   // exact sequential scan of the reference on the per-process rates (global memory; ~never taken)
+        double xi = xi0;
+        jsel = -1;
+        for (int j = 0; j < np; j++) {
+            double nu = (TK == 0) ? chebsum(T.rate + (size_t)T.order * (j + (size_t)np * pre.i), pre, T.order)
+                                  : linear_rate(T.rate, np, j, pre);
+            if (nu > xi) { jsel = j; break; }
+            xi -= nu;
+        }
+        rate_bound_violated = jsel < 0 && !(xi >= 0);
+    }
+    return jsel;
+}
+
+template <int SP, int TK, bool FIRST, bool CB>
+__global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                              unsigned long long* row_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TableView& T = P.tab[SP];
+    const PopView& Q = P.pop[SP];
+    // ---- carve shared memory: particle pool, then the rate table ----
+    WfPool S;
+    unsigned char* ptr = smem_raw;
+    S.d = reinterpret_cast<double*>(ptr); ptr += sizeof(double) * WD_NCOL * WF_THREADS;
+    S.uid = reinterpret_cast<unsigned long long*>(ptr); ptr += 8 * WF_THREADS;
+    S.row = reinterpret_cast<long long*>(ptr); ptr += 8 * WF_THREADS;
+    S.idx = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * WF_THREADS;
+    S.cblock = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * WF_THREADS;
+    S.c2 = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * WF_THREADS;
+    S.c3 = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * WF_THREADS;
+    S.state = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * WF_THREADS;
+    S.cnt = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * 64;
+    S.order = reinterpret_cast<unsigned short*>(ptr); ptr += 2 * WF_THREADS;
+    // pool bytes are a multiple of 16 by construction (see wf_pool_bytes)
+    double* tsm = reinterpret_cast<double*>(smem_raw + WF_POOL_BYTES);
+    // table in shared memory: Chebyshev -> cumulative rows + rate bound + process descriptors; linear -> descriptors only
+    const bool fastsel = (TK == 0) && T.order == 3 && T.nprocs <= 16;
+    const int nrate = (TK == 0) ? (fastsel ? 48 * (T.k + 1) : T.order * T.nprocs * (T.k + 1)) : 0;
+    const int nrb = (TK == 0) ? T.order * (T.k + 1) : 0;
+    {
+        const int nproc_dbl = (T.nprocs * (int)sizeof(ptl_process_desc)) / 8;
+        const double* pd = reinterpret_cast<const double*>(T.procs);
+        if (fastsel) {
+            for (int q = threadIdx.x; q < nrate; q += blockDim.x) {
+                int j = q & 15, m = (q >> 4) % 3, i = q / 48;
+                tsm[q] = j < T.nprocs ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
+            }
+        } else {
+            for (int q = threadIdx.x; q < nrate; q += blockDim.x) tsm[q] = T.cum[q];
+        }
+        for (int q = threadIdx.x; q < nrb; q += blockDim.x) tsm[nrate + q] = T.ratebound[q];
+        for (int q = threadIdx.x; q < nproc_dbl; q += blockDim.x) tsm[nrate + nrb + q] = pd[q];
+    }
+    const double* tcum = (TK == 0) ? tsm : T.cum;
+    SmemTable TS;
+    TS.rate = T.rate;                       // per-process rates stay in global memory (fallback scan only)
+    TS.ratebound = tsm + nrate;
+    TS.procs = reinterpret_cast<const ptl_process_desc*>(tsm + nrate + nrb);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    S.state[tid] = WS_LOAD;
+    const RngCtx rc = {P.step, P.seed_lo, P.seed_hi};
+    const double cut = Q.energy_cut;
+    unsigned long long nsub = 0;
+    __syncthreads();
+
+    for (;;) {
+        // ---- counting sort of the slots by pending work unit (warp ballots -> shared counts) ----
+        const int st = (int)(S.state[tid] & 0xffu);
+        int myrank = 0;
+#pragma unroll
+        for (int c = 0; c < WS_IDLE; c++) {
+            unsigned b = __ballot_sync(0xffffffffu, st == c);
+            if (lane == 0) S.cnt[c * WF_WARPS + wid] = __popc(b);
+            if (st == c) myrank = __popc(b & ltmask);
+        }
+        __syncthreads();
+        // Every warp reduces the 6 x 8 count matrix with its lanes (lane = class*8 + warp): segmented scan over
+        // the warps of a class, then class totals / bases by shuffles.  ~10x fewer instructions than letting each
+        // thread walk the matrix.
+        int e0 = (int)S.cnt[lane];                                 // classes 0..3
+        int e1 = lane < 16 ? (int)S.cnt[32 + lane] : 0;            // classes 4..5
+        int s0 = e0, s1 = e1;
+#pragma unroll
+        for (int d = 1; d < WF_WARPS; d <<= 1) {
+            int t0 = __shfl_up_sync(0xffffffffu, s0, d), t1 = __shfl_up_sync(0xffffffffu, s1, d);
+            if ((lane & (WF_WARPS - 1)) >= d) { s0 += t0; s1 += t1; }
+        }
+        int ncls[WS_IDLE], base[WS_IDLE];
+        ncls[0] = __shfl_sync(0xffffffffu, s0, 7); ncls[1] = __shfl_sync(0xffffffffu, s0, 15);
+        ncls[2] = __shfl_sync(0xffffffffu, s0, 23); ncls[3] = __shfl_sync(0xffffffffu, s0, 31);
+        ncls[4] = __shfl_sync(0xffffffffu, s1, 7); ncls[5] = __shfl_sync(0xffffffffu, s1, 15);
+        int nwork = 0;
+#pragma unroll
+        for (int c = 0; c < WS_IDLE; c++) { base[c] = nwork; nwork += ncls[c]; }
+        if (nwork == 0) break;                     // block-uniform: every slot is idle
+        {
+            int stc = st < WS_IDLE ? st : 0;
+            int before0 = __shfl_sync(0xffffffffu, s0 - e0, ((stc & 3) << 3) + wid);
+            int before1 = __shfl_sync(0xffffffffu, s1 - e1, ((stc & 1) << 3) + wid);
+            int mybase = 0;
+#pragma unroll
+            for (int c = 0; c < WS_IDLE; c++) if (c == stc) mybase = base[c];
+            if (st < WS_IDLE) S.order[mybase + (stc < 4 ? before0 : before1) + myrank] = (unsigned short)tid;
+        }
+        // Chunk scheduling: a warp executes 32 consecutive entries of ONE class, so it never mixes work units.
+        // Full chunks first (class order), then the largest partial chunks; smaller remainders wait for a
+        // later round (they only grow), which keeps ~90 % of the lanes busy with zero intra-warp divergence.
+        int my_c = -1, my_k = 0;
+        {
+            int nfull = 0;
+#pragma unroll
+            for (int c = 0; c < WS_IDLE; c++) {
+                int f = ncls[c] >> 5;
+                if (my_c < 0 && wid < nfull + f) { my_c = c; my_k = wid - nfull; }
+                nfull += f;
+            }
+            if (my_c < 0) {                        // (wid - nfull)-th largest remainder, ranked across lanes 0..5
+                int want = wid - nfull;
+                int key = 0;
+#pragma unroll
+                for (int c = 0; c < WS_IDLE; c++) if (lane == c) key = (ncls[c] & 31) ? (((ncls[c] & 31) << 3) | (WS_IDLE - 1 - c)) : 0;
+                int rank = 0;
+#pragma unroll
+                for (int c = 0; c < WS_IDLE; c++) rank += __shfl_sync(0xffffffffu, key, c) > key;
+                unsigned pick = __ballot_sync(0xffffffffu, lane < WS_IDLE && key > 0 && rank == want);
+                if (pick) {
+                    my_c = __ffs(pick) - 1;
+#pragma unroll
+                    for (int c = 0; c < WS_IDLE; c++) if (c == my_c) my_k = ncls[c] >> 5;
+                }
+            }
+        }
+        __syncthreads();
+
+        int pos = my_k * 32 + lane;
+        bool has = false;
+        int it = 0;
+        if (my_c >= 0) {
+            int nc = 0, bc = 0;
+#pragma unroll
+            for (int c = 0; c < WS_IDLE; c++) if (c == my_c) { nc = ncls[c]; bc = base[c]; }
+            has = pos < nc;
+            if (has) it = (int)S.order[bc + pos];
+        }
+        const uint32_t sw = has ? S.state[it] : (uint32_t)WS_IDLE;
+        const int cls = (int)(sw & 0xffu);
+        const unsigned ldmask = __ballot_sync(0xffffffffu, has && cls == WS_LOAD);
+
+        if (has) {
+            switch (cls) {
+            // ------------------------------------------------------------------------------------------
+            case WS_LOAD: {   // write back the finished particle of this slot (if any), fetch the next row
+                if (sw & WF_VALID) {
+                    long long i = S.row[it];
+                    Q.col[COL_X0][i] = WFD(WD_X0, it); Q.col[COL_X1][i] = WFD(WD_X1, it); Q.col[COL_X2][i] = WFD(WD_X2, it);
+                    Q.col[COL_P0][i] = WFD(WD_P0, it); Q.col[COL_P1][i] = WFD(WD_P1, it); Q.col[COL_P2][i] = WFD(WD_P2, it);
+                    Q.col[COL_T][i] = WFD(WD_T, it); Q.col[COL_S][i] = WFD(WD_S, it); Q.col[COL_R][i] = WFD(WD_R, it);
+                    if (sw & WF_DEAD) Q.active[i] = 0;
+                }
+                int leader = __ffs(ldmask) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(row_counter, (unsigned long long)__popc(ldmask));
+                base = __shfl_sync(ldmask, base, leader);
+                long long i = i0 + (long long)base + __popc(ldmask & ltmask);
+                if (i >= i1) { S.state[it] = WS_IDLE; break; }
+                if (!Q.active[i]) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (mixed_population.jl:63)
+                Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
+                Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+                double t = Q.col[COL_T][i];
+                wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
+                WFD(WD_T, it) = t; WFD(WD_S, it) = Q.col[COL_S][i];
+                WFD(WD_R, it) = FIRST ? setr<SP>(P, TS, p) : Q.col[COL_R][i];     // advance_init!  mixed_population.jl:97-110
+                WFD(WD_TREM, it) = P.tfinal - t;                                   // :65
+                S.uid[it] = Q.uid[i]; S.row[it] = i;
+                S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
+                S.state[it] = WS_STEP | WF_VALID;
+                break;
+            }
+            // ------------------------------------------------------------------------------------------
+            case WS_STEP: {   // one iteration of mixed_population.jl:66-87 up to the process selection
+                double trem = WFD(WD_TREM, it);
+                if (!(trem > DBL_EPS)) { S.state[it] = WS_LOAD | WF_VALID; break; }       // :66
+                double s = WFD(WD_S, it), r = WFD(WD_R, it), t = WFD(WD_T, it);
+                Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
+                double tnext = s / r;                           // :67
+                bool collides = trem > tnext;                   // :68
+                double dt = collides ? tnext : trem;
+                if (!collides) s -= dt * r;                     // :74
+                Vec3 xo = x, po = p;
+                double to = t;
+                push<SP>(P, x, p, t, dt);                       // :77
+                trem -= dt;                                     // :86
+                nsub++;
+                // a free flight ends the step (trem - dt == 0); after a collision the loop test is re-evaluated
+                uint32_t next = collides ? (WS_STEP | WF_VALID) : (WS_LOAD | WF_VALID);
+                bool act = true;
+                Rng rng;
+                bool rng_loaded = false;
+                if (CB) {                                       // onadvance(WallCallback)  callback.jl:167-184
+                    for (int k = 0; k < P.cb.nwalls; k++) {
+                        const ptl_wall_desc& wd = P.cb.wall[k];
+                        if (wd.species != SP) continue;
+                        double xoc = wd.coord == 0 ? xo.x : (wd.coord == 1 ? xo.y : xo.z);
+                        double xnc = wd.coord == 0 ? x.x : (wd.coord == 1 ? x.y : x.z);
+                        if (xoc < wd.v && wd.v < xnc) {
+                            double f = (wd.v - xoc) / (xnc - xoc);
+                            if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
+                            rng.skip();   // lincomb's 4-arg constructor draws (and discards) an s  (electron.jl:127-132)
+                            const WallBuf& W = P.wall[k];
+                            double wgt = Q.col[COL_W][S.row[it]];
+                            unsigned long long slot = atomicAdd(W.n, 1ULL);
+                            if ((long long)slot < W.capacity) {
+                                W.col[0][slot] = x.x * f + xo.x * (1 - f); W.col[1][slot] = x.y * f + xo.y * (1 - f); W.col[2][slot] = x.z * f + xo.z * (1 - f);
+                                W.col[3][slot] = p.x * f + po.x * (1 - f); W.col[4][slot] = p.y * f + po.y * (1 - f); W.col[5][slot] = p.z * f + po.z * (1 - f);
+                                W.col[6][slot] = wgt * f + wgt * (1 - f);
+                                W.col[7][slot] = t * f + to * (1 - f);
+                            } else {
+                                atomicOr(P.flags, PTL_ERR_CAPACITY_OVERFLOW);
+                            }
+                            if (wd.drop) act = false;
+                        }
+                    }
+                }
+                if (!act) next = WS_LOAD | WF_VALID | WF_DEAD;
+                if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
+                    double eng;
+                    if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {                     // :148-151
+                        Pre pre = (TK == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
+                        if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+                        if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
+                        rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
+                        double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;             // :154
+                        const int np = T.nprocs;
+                        bool rbv;
+                        int jsel = fastsel ? wf_select<TK, true>(P, T, tcum, pre, xi, r, rbv) : wf_select<TK, false>(P, T, tcum, pre, xi, r, rbv);   // :166-180
+                        if (rbv) atomicOr(P.flags, PTL_ERR_RATE_BOUND_VIOLATED);            // :186
+                        if (CB && P.cb.count_collisions) atomicAdd(T.counts + (jsel >= 0 ? jsel : np), 1ULL);
+                        int kind = jsel >= 0 ? TS.procs[jsel].kind : PTL_PROC_NULL;
+                        if (kind == PTL_PROC_NULL) {            // NullOutcome: setr! then s = nextcoll()  (:83-88, :182-196)
+                            // setr! recomputes kinenergy and presample from the same p: reuse them
+                            r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : T.maxrate;
+                            s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                        } else {
+                            WFD(WD_ENG, it) = eng;
+                            uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
+                            next = c | WF_VALID | ((uint32_t)jsel << 16);
+                        }
+                    }
+                }
+                if (rng_loaded) wf_store_rng(S, it, rng);
+                wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
+                WFD(WD_T, it) = t; WFD(WD_S, it) = s; WFD(WD_R, it) = r; WFD(WD_TREM, it) = trem;
+                S.state[it] = next;
+                break;
+            }
+            // ------------------------------------------------------------------------------------------
+            case WS_COULOMB: {   // collide(::RelativisticCoulomb) + apply!(StateChange)
+                Rng rng;
+                wf_load_rng(S, it, rng);
+                Vec3 p = wf_get3(S, WD_P0, it);
+                Outcome o;
+                collide_coulomb<SP>(rng, rc, TS.procs[sw >> 16], p, o);
+                wf_store_rng(S, it, rng);
+                wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+                break;
+            }
+            // ------------------------------------------------------------------------------------------
+            case WS_RBEB: {   // rejection trials of rbeb.jl:170-196, two per unit
+                Rng rng;
+                wf_load_rng(S, it, rng);
+                double eng = WFD(WD_ENG, it);
+                double B = TS.procs[sw >> 16].par[0];
+                RbebConsts k = rbeb_consts(eng, B);
+                double w;
+                bool acc = false;
+#pragma unroll 1
+                for (int q = 0; q < 2 && !acc; q++) {
+                    double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+                    double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+                    acc = rbeb_trial(k, u, u2, w);
+                }
+                wf_store_rng(S, it, rng);
+                if (acc) {
+                    WFD(WD_SCR, it) = B * w;      // E2
+                    S.state[it] = WS_IONFIN | WF_VALID | (sw & 0xffff0000u);
+                }
+                break;
+            }
+            // ------------------------------------------------------------------------------------------
+            case WS_IONFIN: {   // rbeb.jl:58-80 after the sampler: kinematics, apply!(NewParticle), birth
+                Rng rng;
+                wf_load_rng(S, it, rng);
+                double eng = WFD(WD_ENG, it), E2 = WFD(WD_SCR, it);
+                double B = TS.procs[sw >> 16].par[0];
+                double E1 = eng - E2 - B;
+                if (!(E2 < E1)) atomicOr(P.flags, PTL_ERR_SAMPLER_INVARIANT);   // @assert E2 < E1  rbeb.jl:63
+                Vec3 p = wf_get3(S, WD_P0, it);
+                Outcome o;
+                ionization_products(rng, rc, p, eng, E1, E2, o);
+                wf_store_rng(S, it, rng);
+                wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+                // add_particle! cut test first (population.jl:105): most secondaries are far below the cut
+                if (P.pop[PTL_ELECTRON].present && E2 > P.pop[PTL_ELECTRON].energy_cut * 0.9) {
+                    uint64_t cu[2];
+                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                    long long i = S.row[it];
+                    add_particle(P, PTL_ELECTRON, wf_get3(S, WD_X0, it), o.p2, Q.col[COL_W][i], WFD(WD_T, it), o.s2, cu[0]);
+                }
+                break;
+            }
+            // ------------------------------------------------------------------------------------------
+            case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
+                Rng rng;
+                wf_load_rng(S, it, rng);
+                Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
+                double eng = WFD(WD_ENG, it), t = WFD(WD_T, it);
+                Outcome o;
+                collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
+                wf_store_rng(S, it, rng);
+                long long i = S.row[it];
+                uint64_t cu[2];
+                switch (o.kind) {
+                case OUT_NULL:
+                    WFD(WD_R, it) = setr<SP>(P, TS, p);
+                    WFD(WD_S, it) = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                    wf_store_rng(S, it, rng);
+                    S.state[it] = WS_STEP | WF_VALID;
+                    break;
+                case OUT_STATE_CHANGE:
+                    wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+                    break;
+                case OUT_NEW_PARTICLE:
+                    wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+                    break;
+                case OUT_REMOVE:
+                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+                    break;
+                case OUT_REPLACE:
+                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+                    break;
+                case OUT_REPLACE_PAIR:
+                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+                    add_particle(P, o.sp3, x, o.p3, Q.col[COL_W][i], t, o.s3, cu[1]);
+                    break;
+                }
+                break;
+            }
+            default: break;
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
+    if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+}
+
+}  // namespace ptl

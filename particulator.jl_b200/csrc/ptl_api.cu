@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ptl_advance.cuh"
+#include "ptl_advance_wf.cuh"
 #include "ptl_store.cuh"
 
 using namespace ptl;
@@ -30,7 +31,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
 struct Table {
     TableView v{};
     std::vector<ptl_process_desc> procs;
-    double *d_rate = nullptr, *d_rb = nullptr;
+    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr;
     ptl_process_desc* d_procs = nullptr;
     unsigned long long* d_counts = nullptr;
     size_t smem_bytes = 0;
@@ -199,10 +200,52 @@ int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0,
     return 0;
 }
 
+// wavefront variant (collision-dominated species): persistent CTAs, shared-memory particle pool
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem) {
+    auto kern = k_advance_wf<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? 48 : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    (void)table_smem;
+    size_t smem = wf_pool_bytes() + tsm + 32;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        configured = true;
+    }
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WF_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long rows = i1 - i0;
+    long long want = (rows + WF_THREADS - 1) / WF_THREADS;
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
+    CK(cudaGetLastError());
+    ctx->stats.launches++;
+    return 0;
+}
+
+template <int SP, bool FIRST, bool CB>
+int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem) {
+    if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem);
+    return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem);
+}
+
+// photons (kappa << 1, HBM-bound) stream through the one-particle-per-lane kernel; collision-dominated species
+// (electrons, positrons, slow electrons) go through the wavefront kernel.  One variant per species is compiled.
 template <int SP>
 int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
-    if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem);
-    return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem);
+    if constexpr (SP == PTL_PHOTON) {
+        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem);
+        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem);
+    } else {
+        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem);
+        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem);
+    }
 }
 
 int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
@@ -266,7 +309,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     if (!ctx) return PTL_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_procs); cudaFree(t.d_counts); }
+    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_cum); cudaFree(t.d_procs); cudaFree(t.d_counts); }
     for (auto& p : ctx->pops) if (p.block) cudaFree(p.block);
     for (auto& s : ctx->sbs) { cudaFree((void*)s.v.log_energy); cudaFree((void*)s.v.data); }
     for (auto& c : ctx->cls) { cudaFree((void*)c.v.ec); cudaFree((void*)c.v.pc); }
@@ -360,6 +403,20 @@ EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t np
     int32_t rc = upload_doubles(ctx, rate, (size_t)order * nprocs * (k + 1), &T.d_rate); if (rc) return rc;
     rc = upload_doubles(ctx, ratebound, (size_t)order * (k + 1), &T.d_rb); if (rc) return rc;
     T.v.rate = T.d_rate; T.v.ratebound = T.d_rb;
+    {   // running sums over the (sorted) processes: cum[m, j, i] = sum_{j' <= j} rate[m, j', i]
+        std::vector<double> cum((size_t)order * nprocs * (k + 1));
+        for (int i = 0; i <= k; i++)
+            for (int m = 0; m < order; m++) {
+                double acc = 0;
+                for (int j = 0; j < nprocs; j++) {
+                    size_t q = (size_t)m + (size_t)order * ((size_t)j + (size_t)nprocs * i);
+                    acc += rate[q];
+                    cum[q] = acc;
+                }
+            }
+        rc = upload_doubles(ctx, cum.data(), cum.size(), &T.d_cum); if (rc) return rc;
+        T.v.cum = T.d_cum;
+    }
     rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
     T.smem_bytes = sizeof(double) * ((size_t)order * nprocs * (k + 1) + (size_t)order * (k + 1)) + sizeof(ptl_process_desc) * nprocs;
     if (T.smem_bytes > 60 * 1024) { ctx->err = "Chebyshev table too large for shared memory"; return PTL_EINVAL; }
@@ -374,6 +431,15 @@ EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, doub
     T.v.kind = 1; T.v.grid_kind = grid_kind; T.v.L1 = L1; T.v.L2 = L2; T.v.nE = nE; T.v.maxrate = maxrate;
     int32_t rc = upload_doubles(ctx, rate, (size_t)nprocs * nE, &T.d_rate); if (rc) return rc;
     T.v.rate = T.d_rate;
+    {   // cum[j, e] = sum_{j' <= j} rate[j', e]
+        std::vector<double> cum((size_t)nprocs * nE);
+        for (int e = 0; e < nE; e++) {
+            double acc = 0;
+            for (int j = 0; j < nprocs; j++) { acc += rate[j + (size_t)nprocs * e]; cum[j + (size_t)nprocs * e] = acc; }
+        }
+        rc = upload_doubles(ctx, cum.data(), cum.size(), &T.d_cum); if (rc) return rc;
+        T.v.cum = T.d_cum;
+    }
     rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
     T.smem_bytes = sizeof(ptl_process_desc) * nprocs;
     ctx->tables.push_back(T);

@@ -24,6 +24,10 @@ constexpr double CO_RE = (CO_E * CO_E) / (CO_ME * (CO_C * CO_C)) / (4 * CO_PI * 
 constexpr double CO_A0 = CO_HBAR / (CO_ME * CO_C * CO_ALPHA);                               // :160
 constexpr double CO_MC2 = CO_ME * (CO_C * CO_C);                                            // :163
 constexpr double CO_C2 = CO_C * CO_C;
+constexpr double INV_MC2 = 1.0 / CO_MC2;
+constexpr double INV_C = 1.0 / CO_C;
+constexpr double INV_ME = 1.0 / CO_ME;
+constexpr double C2_OVER_MC2SQ = CO_C2 / (CO_MC2 * CO_MC2);
 constexpr double DBL_EPS = 2.220446049250313e-16;     // eps(Float64), mixed_population.jl:66
 
 constexpr int MAX_ORDER = 8;
@@ -50,6 +54,7 @@ struct TableView {
     double xmax;
     const double* rate;              // cheb: [order, nprocs, k+1]; linear: [nprocs, nE]
     const double* ratebound;         // cheb: [order, k+1]
+    const double* cum;               // running sum over processes of `rate` (same layout): selection accelerator
     int grid_kind, nE;
     double L1, L2, maxrate;
     const ptl_process_desc* procs;   // device copy
@@ -123,6 +128,14 @@ __device__ __forceinline__ double bits_to_u01(uint32_t lo, uint32_t hi) {
     return __hiloint2double((int)dhi, (int)dlo) + (-1.0 + 0x1.0p-53);
 }
 
+// One Philox block as a real function: the advance kernels draw at ~70 sites and inlining the ten
+// rounds everywhere blew the kernel up to 300 KB of SASS (instruction-cache misses were the top stall).
+__device__ __noinline__ uint4 philox_block(uint32_t block, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, uint32_t k0, uint32_t k1) {
+    uint32_t o[4];
+    philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // Per-particle stream: replaces the task-local rand() of the reference (src/util.jl:17 and every
 // collide).  The n-th uniform of (uid, advance call) is word pair (n & 1) of block n >> 1.
 struct Rng {
@@ -140,32 +153,26 @@ struct Rng {
     }
     __device__ __forceinline__ double u(uint32_t step, uint32_t seed_lo, uint32_t seed_hi) {
         uint32_t block = idx >> 1;
-        double r;
-        if (idx & 1) {
-            if (cblock != block) {
-                uint32_t o[4];
-                philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
-                c2 = o[2]; c3 = o[3]; cblock = block;
-            }
-            r = bits_to_u01(c2, c3);
+        uint32_t lo, hi;
+        if ((idx & 1) && cblock == block) {
+            lo = c2; hi = c3;
         } else {
-            uint32_t o[4];
-            philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
-            c2 = o[2]; c3 = o[3]; cblock = block;
-            r = bits_to_u01(o[0], o[1]);
+            uint4 o = philox_block(block, step, seed_lo, seed_hi, k0, k1);
+            c2 = o.z; c3 = o.w; cblock = block;
+            lo = (idx & 1) ? o.z : o.x;
+            hi = (idx & 1) ? o.w : o.y;
         }
         idx++;
-        return r;
+        return bits_to_u01(lo, hi);
     }
     __device__ __forceinline__ void skip() { idx++; }
 };
 
 __device__ __forceinline__ void child_uids(uint64_t parent, uint32_t idx, uint32_t step, uint32_t seed_lo, uint32_t seed_hi,
                                            uint64_t out[2]) {
-    uint32_t o[4];
-    philox4x32_10(idx, step, seed_lo, seed_hi, (uint32_t)parent, (uint32_t)(parent >> 32) ^ DOM_CHILD_UID, o);
-    out[0] = ((uint64_t)o[1] << 32) | o[0];
-    out[1] = ((uint64_t)o[3] << 32) | o[2];
+    uint4 o = philox_block(idx, step, seed_lo, seed_hi, (uint32_t)parent, (uint32_t)(parent >> 32) ^ DOM_CHILD_UID);
+    out[0] = ((uint64_t)o.y << 32) | o.x;
+    out[1] = ((uint64_t)o.w << 32) | o.z;
 }
 
 }  // namespace ptl
