@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the advance hot path on N B200s (one process per GPU).
+
+Workload (BASELINE.json configs[2]): relativistic runaway electron avalanche,
+electrons with E ~ exp(-E/7.3 MeV) on [1 keV, 100 MeV], cos(theta_z) ~ U[0.8, 1], uniform E_z = -5e5 V/m, STP air
+(Coulomb + Seltzer-Berger + RBEB tables of scripts/beam.jl:94-105, safety 1.15), dt = 2.5e-11 s, photon and
+positron populations start empty.  One "step" = what run! does per dt (src/run.jl:6-9): advance!(mpopl, pusher, t+dt)
+followed by droplow! on every population.  A particle-step = one particle alive at the start of a step carried
+through it.  Per-GPU work is fixed (weak scaling): N GPUs hold N x n_per_gpu electrons, sharded with no
+data-path collective; NCCL only reduces the diagnostics at the end.
+
+  value     whole-job particle-steps/s, state resident in HBM (timed with CUDA events, max over ranks)
+  e2e       the same through the C-ABI with HOST buffers: pinned host arrays -> ptl_population_upload ->
+            ptl_advance -> ptl_droplow -> ptl_population_download, copies inside the timed region
+  roofline  dominant kernel (electron advance, first pass): algorithmic bytes = 162 B per particle-step
+             / its cudaEvent duration, against the measured HBM copy bandwidth
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm, OpenMP over all host cores) on a bounded
+            sample of the same workload — a reported baseline, not the target
+`--impl reference` times that CPU restatement alone (Julia is not installable in this image)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT = 2.5e-11
+EFIELD = 5e5
+ALGO_BYTES_PER_PARTICLE_STEP = 162.0     # 81 B read + 81 B write
+
+
+def build_tables(P):
+    co = P.co
+    comp = P.air_composition()
+    Fdt = co.elementary_charge * EFIELD * DT
+    return {"electron": P.build_electron_collision_table(comp, Fdt, safety=1.15),
+            "positron": P.build_positron_collision_table(comp, 1e2 * co.eV, Fdt, safety=1.15),
+            "photon": P.build_photon_collision_table(comp)}
+
+
+def synth_electrons_numpy(P, n, seed, uid0):
+    """RREA spectrum, host arrays (used by the CPU legs and as the pinned e2e source)."""
+    co = P.co
+    rng = np.random.default_rng(seed)
+    K = np.clip(rng.exponential(7.3e6, n), 1e3 * 1.0001, 1e8) * co.eV
+    pn = P.momentum_norm_from_kin(P.ELECTRON, K)
+    cost = rng.uniform(0.8, 1.0, n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    sint = np.sqrt(1 - cost ** 2)
+    p = np.stack([sint * np.cos(phi), sint * np.sin(phi), cost], axis=1) * pn[:, None]
+    return dict(x=np.zeros((n, 3)), p=p, w=np.ones(n), t=np.zeros(n), s=-np.log(1 - rng.random(n)), r=np.zeros(n),
+                active=np.ones(n, dtype=np.uint8), uid=np.arange(uid0, uid0 + n, dtype=np.uint64))
+
+
+class _DevArray:
+    """Zero-copy view of a library-owned device column for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def column_tensor(torch, pop, col, n):
+    typestr = "<f8" if col < 10 else ("|u1" if col == 10 else "<i8")      # uid viewed as int64 (same bits)
+    return torch.as_tensor(_DevArray(pop.column_ptr(col), n, typestr), device="cuda")
+
+
+def synth_electrons_device(torch, P, pop, n, seed, uid0):
+    """Same distribution generated on the device straight into the library's SoA columns."""
+    co = P.co
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    u = lambda: torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+    K = torch.clamp(-7.3e6 * torch.log1p(-u()), 1e3 * 1.0001, 1e8) * co.eV
+    pn = torch.sqrt((K + co.electron_mc2) ** 2 - co.electron_mc2 ** 2) / co.c
+    cost = 0.8 + 0.2 * u()
+    phi = 2 * np.pi * u()
+    sint = torch.sqrt(1 - cost ** 2)
+    cols = [torch.zeros(n, device="cuda", dtype=torch.float64)] * 3 + [pn * sint * torch.cos(phi), pn * sint * torch.sin(phi), pn * cost]
+    cols += [torch.ones(n, device="cuda", dtype=torch.float64), torch.zeros(n, device="cuda", dtype=torch.float64),
+             -torch.log1p(-u()), torch.zeros(n, device="cuda", dtype=torch.float64)]
+    for c, v in enumerate(cols):
+        column_tensor(torch, pop, c, n).copy_(v)
+    column_tensor(torch, pop, 10, n).fill_(1)
+    column_tensor(torch, pop, 11, n).copy_(torch.arange(n, device="cuda", dtype=torch.int64) + uid0)
+    torch.cuda.synchronize()
+    pop.set_n(n)
+
+
+def make_world(P, ctx, tables, cap_e, cap_g, cap_p):
+    co = P.co
+    el = P.Population(ctx, P.ELECTRON, cap_e, None, tables["electron"], 1e3 * co.eV)
+    ph = P.Population(ctx, P.PHOTON, cap_g, None, tables["photon"], 1e3 * co.eV)
+    po = P.Population(ctx, P.POSITRON, cap_p, None, tables["positron"], 1e2 * co.eV)
+    mp = P.MultiPopulation(("electron", el), ("photon", ph), ("positron", po))
+    return mp, el, ph, po
+
+
+def pusher(P):
+    return P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -EFIELD]), P.HomogeneousField([0.0, 0.0, 0.0])))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_leg(P, tables, n_sample, steps, warmup, seed=0):
+    """Time the CPU oracle (test infrastructure, used here only as the reported baseline) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_backend import oracle_context, oracle_backend
+    ctx = oracle_context()
+    cores = int(oracle_backend().dll.ora_num_threads())
+    mp, el, ph, po = make_world(P, ctx, tables, int(1.5 * n_sample) + 1024, n_sample + 1024, n_sample // 4 + 1024)
+    el.upload(synth_electrons_numpy(P, n_sample, seed, 1))
+    ctx.set_rng(seed, 0)
+    psh = pusher(P)
+    t = 0.0
+    psteps, sub, el_t = 0, 0, 0.0
+    times = []
+    for it in range(warmup + steps):
+        n0 = len(el)
+        t0 = time.perf_counter()
+        t += DT
+        P.advance(mp, psh, t)
+        for q in mp:
+            P.droplow(q)
+        dtm = time.perf_counter() - t0
+        if it >= warmup:
+            psteps += n0
+            sub += P.last_advance_stats(mp)["substeps"]
+            el_t += dtm
+            times.append(dtm)
+    ctx.close()
+    return {"value": psteps / el_t, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_sample} electrons of the same RREA spectrum x {steps} steps (after {warmup} warm-up) through the C "
+                      f"restatement of the reference algorithm (oracle/), OpenMP static schedule; Julia is not installable here",
+            "kappa": sub / max(psteps, 1), "substeps_per_s": sub / el_t, "ms_per_step": 1e3 * el_t / max(len(times), 1)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-per-gpu", type=int, default=int(os.environ.get("PTL_BENCH_N", 100_000_000)))
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    import particulator_b200 as P
+    config = {"workload": "RREA electron avalanche in STP air (BASELINE.json configs[2]): E~exp(-E/7.3MeV) on [1 keV,100 MeV], "
+                          "uniform E_z=-5e5 V/m, dt=2.5e-11 s, e-/gamma/e+ populations, advance!+droplow! per step",
+              "electrons_per_gpu": args.n_per_gpu, "electrons_total": args.n_per_gpu * max(world, 1), "dt_s": DT,
+              "parallelism": f"particle-sharded x{max(world, 1)}, no data-path collective",
+              "l2_policy": "inputs larger than L2 (>= 8.9 GB of particle state per GPU)"}
+
+    # ------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        tables = build_tables(P)
+        res = cpu_leg(P, tables, args.cpu_sample, max(args.steps, 1), max(args.warmup, 1))
+        config["electrons_per_gpu"] = args.cpu_sample
+        config["electrons_total"] = args.cpu_sample
+        config["note"] = "reference arm = CPU restatement of the reference algorithm on a bounded sample of the same workload"
+        line = {"metric": "particle-steps/sec", "value": res["value"], "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference", "cpu_baseline": res,
+                "e2e": {"value": res["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "kappa": res["kappa"], "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    tables = build_tables(P)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = P.Context(device=local_rank, stream=stream)
+    ctx.set_profiling(True)
+    n = args.n_per_gpu
+    cap_e = int(1.6 * n) + 4096       # room for the in-step births (~10 %) and the quasi-steady keV secondaries
+    mp, el, ph, po = make_world(P, ctx, tables, cap_e, max(n // 2, 1 << 20), max(n // 16, 1 << 18))
+    uid0 = 1 + rank * (1 << 40)
+    synth_electrons_device(torch, P, el, n, seed=1234 + rank, uid0=uid0)
+    ctx.set_rng(rank, 0)           # uid-keyed Philox: shards are independent through their uids; seed also differs
+    psh = pusher(P)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    t = 0.0
+
+    def step():
+        nonlocal t
+        n0 = len(el)
+        t += DT
+        P.advance(mp, psh, t)
+        st = P.last_advance_stats(mp)
+        for q in mp:
+            P.droplow(q)
+        return n0, st
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    psteps = substeps = 0
+    main_ms = main_rows = 0.0
+    for _ in range(args.steps):
+        n0, st = step()
+        psteps += n0
+        substeps += st["substeps"]
+        main_ms += st["main_ms"]
+        main_rows += st["main_rows"]
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    tot = torch.tensor([float(psteps), float(substeps), float(launches)], device="cuda", dtype=torch.float64)
+    mx = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    psteps_all, substeps_all, launches_all = (float(v) for v in tot.tolist())
+    elapsed_all = float(mx.item())
+    value = psteps_all / (elapsed_all * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank) ----
+    peak, peak_src = measured_hbm_peak()
+    achieved = (ALGO_BYTES_PER_PARTICLE_STEP * main_rows) / (main_ms * 1e-3) / 1e9 if main_ms > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic = tj["dram_bytes_per_row"] * (main_rows / max(args.steps, 1))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_advance_wf<electron> (first pass)",
+                "kernel_ms_per_launch": main_ms / max(args.steps, 1), "rows_per_launch": main_rows / max(args.steps, 1),
+                "algorithmic_bytes_per_row": ALGO_BYTES_PER_PARTICLE_STEP,
+                "note": "electrons in STP air do kappa collision sub-steps per particle-step; the kernel is instruction-issue bound, "
+                        "not HBM bound, whenever kappa >> 1 (see DESIGN.md section 6); kappa is reported below"}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        n_now = len(el)
+        if psutil.virtual_memory().available < 3.2 * 89 * n_now:      # host RAM guard: e2e keeps two pinned copies
+            keep = int(psutil.virtual_memory().available / (3.2 * 89))
+            el.set_n(keep)
+            config["e2e_note"] = f"host RAM limited the e2e leg to {keep} of {n_now} electrons"
+        d = el.download()
+        n_e2e = len(d["w"])
+        host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()}
+        out = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+        del d
+        import ctypes as C
+        b = ctx.backend
+
+        def ptr(tn, ty):
+            return C.cast(tn.data_ptr(), C.POINTER(ty))
+
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_psteps = 0
+        pd = psh.desc(ctx)
+        for k in range(args.e2e_steps):
+            rc = b.population_upload(ctx.h, el.id, n_e2e, ptr(host["x"], C.c_double), ptr(host["p"], C.c_double), ptr(host["w"], C.c_double),
+                                     ptr(host["t"], C.c_double), ptr(host["s"], C.c_double), ptr(host["r"], C.c_double),
+                                     ptr(host["active"], C.c_uint8), ptr(host["uid"], C.c_uint64))
+            assert rc == 0, rc
+            t_loc = float(host["t"][0]) + DT
+            rc = b.advance(ctx.h, mp.id, C.byref(pd), t_loc, None)
+            assert rc >= 0, rc
+            for q in mp:
+                b.droplow(ctx.h, q.id, 0.0)
+            got = b.population_download(ctx.h, el.id, n_e2e, ptr(out["x"], C.c_double), ptr(out["p"], C.c_double), ptr(out["w"], C.c_double),
+                                        ptr(out["t"], C.c_double), ptr(out["s"], C.c_double), ptr(out["r"], C.c_double),
+                                        ptr(out["active"], C.c_uint8), ptr(out["uid"], C.c_uint64))
+            assert got > 0
+            e2e_psteps += n_e2e
+        f1.record()
+        barrier()
+        e2e_ms = torch.tensor([f0.elapsed_time(f1)], device="cuda", dtype=torch.float64)
+        e2e_ps = torch.tensor([float(e2e_psteps)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e2e_ps, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(e2e_ps.item()) / (float(e2e_ms.item()) * 1e-3), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": 89 * n_e2e, "d2h_bytes_per_step": 89 * min(n_e2e, int(got)), "steps": args.e2e_steps,
+               "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download"}
+
+    # ---- CPU baseline on the host cores of this box (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_leg(P, tables, args.cpu_sample, 2, 1)
+
+    if rank == 0:
+        line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": max(world, 1), "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
+                "kappa": substeps_all / max(psteps_all, 1.0), "substeps_per_s": substeps_all / (elapsed_all * 1e-3),
+                "hbm_roofline_frac_whole_step": (ALGO_BYTES_PER_PARTICLE_STEP * value / max(world, 1)) / 1e9 / peak}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

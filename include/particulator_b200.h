@@ -301,8 +301,15 @@ typedef struct {
     int64_t rows;
     int64_t births;
     int64_t launches;   /* kernels launched by the call */
+    int64_t main_rows;  /* rows of the largest advance-kernel launch of the call */
+    double  main_ms;    /* its duration, measured with CUDA events on the context's stream (0 unless profiling is on) */
 } ptl_advance_stats;
 int32_t ptl_last_advance_stats(ptl_context* ctx, ptl_advance_stats* out);
+
+/* Measurement aids: cudaEvent timing of the dominant advance kernel (reported in ptl_advance_stats.main_ms)
+ * and the number of kernels this context has launched since the last reset. */
+int32_t ptl_set_profiling(ptl_context* ctx, int32_t on);
+int64_t ptl_launch_count(ptl_context* ctx, int32_t reset);
 
 /* CollisionCounter read-out (callback.jl:118-141): counts[nprocs+1] per table (last = null). */
 int32_t ptl_collision_counts(ptl_context* ctx, int32_t table, int64_t* counts, int32_t clear);

@@ -1471,6 +1471,8 @@ EXPORT int32_t ora_advance(ora_context* ctx, int32_t mp, const ptl_pusher_desc* 
     return ctx->flags;
 }
 
+EXPORT int32_t ora_set_profiling(ora_context* ctx, int32_t on) { (void)ctx; (void)on; return 0; }
+EXPORT int64_t ora_launch_count(ora_context* ctx, int32_t reset) { (void)ctx; (void)reset; return 0; }
 EXPORT int32_t ora_last_advance_stats(ora_context* ctx, ptl_advance_stats* out) { *out = ctx->stats; return 0; }
 
 EXPORT int32_t ora_collision_counts(ora_context* ctx, int32_t table, int64_t* counts, int32_t clear) {

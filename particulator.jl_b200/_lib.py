@@ -52,7 +52,7 @@ class DiagOut(C.Structure):
 
 class AdvanceStats(C.Structure):
     _fields_ = [("passes", C.c_int64), ("substeps", C.c_int64), ("rows", C.c_int64), ("births", C.c_int64),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("main_rows", C.c_int64), ("main_ms", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -98,6 +98,8 @@ _SIGS = {
     "init": (C.c_int32, [_vp, C.c_int32]),
     "advance": (C.c_int32, [_vp, C.c_int32, C.POINTER(PusherDesc), C.c_double, C.POINTER(CallbackDesc)]),
     "last_advance_stats": (C.c_int32, [_vp, C.POINTER(AdvanceStats)]),
+    "set_profiling": (C.c_int32, [_vp, C.c_int32]),
+    "launch_count": (C.c_int64, [_vp, C.c_int32]),
     "collision_counts": (C.c_int32, [_vp, C.c_int32, _i64p, C.c_int32]),
     "wall_records": (C.c_int64, [_vp, C.c_int32, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32]),
     "collide_test": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_uint64, _dp]),

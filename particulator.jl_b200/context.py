@@ -54,6 +54,12 @@ class Context:
     def error_flags(self, clear=False):
         return self.backend.error_flags(self.h, 1 if clear else 0)
 
+    def set_profiling(self, on=True):
+        self.check(self.backend.set_profiling(self.h, 1 if on else 0), "set_profiling")
+
+    def launch_count(self, reset=False):
+        return int(self.backend.launch_count(self.h, 1 if reset else 0))
+
     def synchronize(self):
         self.check(self.backend.synchronize(self.h), "synchronize")
 

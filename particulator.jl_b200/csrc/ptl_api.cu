@@ -91,6 +91,10 @@ struct ptl_context {
     int partial_blocks = 0;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_pending = false;
 };
 
 namespace {
@@ -101,6 +105,7 @@ bool cuda_ok(ptl_context* ctx, cudaError_t e, const char* what) {
     return false;
 }
 #define CK(call) do { if (!cuda_ok(ctx, (call), #call)) return PTL_ECUDA; } while (0)
+#define LAUNCHED() do { ctx->launch_total++; CK(cudaGetLastError()); } while (0)
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -194,8 +199,11 @@ int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0,
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
     kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
-    CK(cudaGetLastError());
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
     ctx->stats.launches++;
     return 0;
 }
@@ -223,8 +231,11 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
     kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
-    CK(cudaGetLastError());
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
     ctx->stats.launches++;
     return 0;
 }
@@ -319,6 +330,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp);
     cudaFree(ctx->d_sc);
     cudaFreeHost(ctx->h_sc);
+    if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -470,7 +482,7 @@ EXPORT int32_t ptl_table_eval(ptl_context* ctx, int32_t table, int64_t n, const 
     double* d_r = d_b + n;
     CK(cudaMemcpyAsync(d_e, energy, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     k_table_eval<<<grid_for(n, 128), 128, 0, ctx->stream>>>(T.v, n, d_e, d_r, d_b, &ctx->d_sc->flags);
-    CK(cudaGetLastError());
+    LAUNCHED();
     if (T.v.nprocs) CK(cudaMemcpyAsync(rates_out, d_r, sizeof(double) * n * T.v.nprocs, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(bound_out, d_b, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -533,7 +545,7 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
             CK(cudaMemcpyAsync(ctx->stage[b], src + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
             k_aos3_to_planar<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[b], P->v.col[c0] + off, P->v.col[c0 + 1] + off,
                                                                         P->v.col[c0 + 2] + off, m);
-            CK(cudaGetLastError());
+            LAUNCHED();
             b ^= 1;
         }
     }
@@ -547,7 +559,7 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
             CK(cudaMemcpyAsync(P->v.uid, uid, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         } else {
             k_fill_uid<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.uid, ctx->next_uid, n);
-            CK(cudaGetLastError());
+            LAUNCHED();
         }
     }
     ctx->next_uid += (uint64_t)n;
@@ -575,7 +587,7 @@ EXPORT int64_t ptl_population_download(ptl_context* ctx, int32_t pop, int64_t ma
             long long m = n - off < (long long)ctx->stage_rows ? n - off : (long long)ctx->stage_rows;
             k_planar_to_aos3<<<grid_for(m, 256), 256, 0, ctx->stream>>>(P->v.col[c0] + off, P->v.col[c0 + 1] + off, P->v.col[c0 + 2] + off,
                                                                         (double*)ctx->stage[b], m);
-            CK(cudaGetLastError());
+            LAUNCHED();
             CK(cudaMemcpyAsync(dst + 3 * off, ctx->stage[b], sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, ctx->stream));
             b ^= 1;
         }
@@ -677,9 +689,9 @@ int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
     }
     double th = thres == 0 ? P.v.energy_cut : thres;   // population.jl:274
     DISPATCH_SPECIES(P.v.species, k_flag_count<SP><<<(unsigned)ntiles, CMP_THREADS, 0, ctx->stream>>>(P.v, n, th, do_flag ? 1 : 0, ctx->d_tile_counts));
-    CK(cudaGetLastError());
+    LAUNCHED();
     k_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_counts, ntiles, ctx->d_tile_offsets, &ctx->d_sc->total);
-    CK(cudaGetLastError());
+    LAUNCHED();
     CK(cudaMemsetAsync(&ctx->d_sc->nmoves, 0, sizeof(unsigned long long), ctx->stream));
     rc = sync_scalars(ctx); if (rc) return rc;
     long long total = (long long)ctx->h_sc->total;
@@ -694,9 +706,9 @@ int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
         }
         k_emit_moves<<<(unsigned)ntiles, CMP_THREADS, 0, ctx->stream>>>(P.v, n, ctx->d_tile_offsets, &ctx->d_sc->total, ctx->d_holes, ctx->d_tails,
                                                                          &ctx->d_sc->nmoves);
-        CK(cudaGetLastError());
+        LAUNCHED();
         k_apply_moves<<<grid_for(max_moves, 256), 256, 0, ctx->stream>>>(P.v, ctx->d_holes, ctx->d_tails, &ctx->d_sc->nmoves);
-        CK(cudaGetLastError());
+        LAUNCHED();
     }
     rc = set_n(ctx, P, total); if (rc) return rc;
     return total;
@@ -728,9 +740,9 @@ EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
     int blocks = (int)((n + DIAG_THREADS - 1) / DIAG_THREADS);
     if (blocks > ctx->partial_blocks) blocks = ctx->partial_blocks;
     DISPATCH_SPECIES(P->v.species, k_diag_partial<SP><<<blocks, DIAG_THREADS, 0, ctx->stream>>>(P->v, n, ctx->d_partial));
-    CK(cudaGetLastError());
+    LAUNCHED();
     k_diag_final<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, blocks, ctx->d_sc->diag);
-    CK(cudaGetLastError());
+    LAUNCHED();
     rc = sync_scalars(ctx); if (rc) return rc;
     const double* d = ctx->h_sc->diag;
     out->nactive = (int64_t)llround(d[0]);
@@ -754,7 +766,7 @@ EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, do
         if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
         DISPATCH_SPECIES(P->v.species, k_histogram<SP><<<blocks, 256, sizeof(double) * nbins, ctx->stream>>>(P->v, n, quantity, lo, hi, nbins, logscale,
                                                                                                              (double*)ctx->d_tmp));
-        CK(cudaGetLastError());
+        LAUNCHED();
     }
     CK(cudaMemcpyAsync(out, ctx->d_tmp, sizeof(double) * nbins, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -768,7 +780,7 @@ EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
     int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
     if (n > 0) {
         k_roulette<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32));
-        CK(cudaGetLastError());
+        LAUNCHED();
     }
     ctx->step++;
     return 0;
@@ -781,7 +793,7 @@ EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
     int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
     if (n > 0) {
         k_split<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), &ctx->d_sc->flags);
-        CK(cudaGetLastError());
+        LAUNCHED();
     }
     ctx->step++;
     rc = read_n(ctx, *P, &n); if (rc) return rc;
@@ -817,7 +829,7 @@ EXPORT int32_t ptl_init(ptl_context* ctx, int32_t mp) {
         long long n = (long long)ctx->h_sc->pop_n[P.slot];
         if (n <= 0) continue;
         DISPATCH_SPECIES(P.v.species, k_init_r<SP><<<grid_for(n, 256), 256, 0, ctx->stream>>>(A, n));
-        CK(cudaGetLastError());
+        LAUNCHED();
     }
     rc = sync_scalars(ctx); if (rc) return rc;
     return ctx->h_sc->flags;
@@ -887,9 +899,31 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
         if (total == 0) break;     // advance1! returned 0 (mixed_population.jl:44-46)
     }
     ctx->step++;
+    if (ctx->ev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.main_ms = ms;
+        ctx->ev_pending = false;
+    }
     ctx->stats.substeps = (int64_t)ctx->h_sc->substeps;
     ctx->stats.births = (int64_t)ctx->h_sc->births;
     return ctx->h_sc->flags;
+}
+
+EXPORT int32_t ptl_set_profiling(ptl_context* ctx, int32_t on) {
+    if (!ctx) return PTL_EINVAL;
+    if (on && !ctx->ev0) {
+        CK(cudaEventCreate(&ctx->ev0));
+        CK(cudaEventCreate(&ctx->ev1));
+    }
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+EXPORT int64_t ptl_launch_count(ptl_context* ctx, int32_t reset) {
+    if (!ctx) return PTL_EINVAL;
+    long long v = ctx->launch_total;
+    if (reset) ctx->launch_total = 0;
+    return v;
 }
 
 EXPORT int32_t ptl_last_advance_stats(ptl_context* ctx, ptl_advance_stats* out) {
@@ -923,7 +957,7 @@ EXPORT int64_t ptl_wall_records(ptl_context* ctx, int32_t iwall, int64_t max_n, 
             if (!dst) continue;
             int c0 = which * 3;
             k_planar_to_aos3<<<grid_for(n, 256), 256, 0, ctx->stream>>>(W.b.col[c0], W.b.col[c0 + 1], W.b.col[c0 + 2], (double*)ctx->d_tmp, n);
-            CK(cudaGetLastError());
+            LAUNCHED();
             CK(cudaMemcpyAsync(dst, ctx->d_tmp, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (w) CK(cudaMemcpyAsync(w, W.b.col[6], sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -950,7 +984,7 @@ EXPORT int32_t ptl_collide_test(ptl_context* ctx, int32_t species, int32_t table
     double* d_o = d_p + 3 * n;
     CK(cudaMemcpyAsync(d_p, p3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
     DISPATCH_SPECIES(species, k_collide_test<SP><<<grid_for(n, 128), 128, 0, ctx->stream>>>(A, T.v, j, n, d_p, uid0, d_o));
-    CK(cudaGetLastError());
+    LAUNCHED();
     CK(cudaMemcpyAsync(out, d_o, sizeof(double) * 24 * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -969,7 +1003,7 @@ EXPORT int32_t ptl_rng_test(ptl_context* ctx, uint64_t uid, uint64_t seed, uint3
     if (n == 0) return 0;
     int32_t rc = ensure_tmp(ctx, sizeof(double) * n); if (rc) return rc;
     k_rng_test<<<1, 1, 0, ctx->stream>>>(uid, step, (uint32_t)seed, (uint32_t)(seed >> 32), n, (double*)ctx->d_tmp);
-    CK(cudaGetLastError());
+    LAUNCHED();
     CK(cudaMemcpyAsync(out, ctx->d_tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
