@@ -195,9 +195,9 @@ typedef struct {
 } wallrec_t;
 
 #define MAX_TABLES 16
-#define MAX_POPS 16
+#define MAX_POPS 64
 #define MAX_SB 8
-#define MAX_MP 4
+#define MAX_MP 32
 #define MAX_CHEBLOSS 4
 
 typedef struct ora_context {

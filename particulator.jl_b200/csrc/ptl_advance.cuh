@@ -26,7 +26,7 @@ struct SmemTable {
 };
 
 // add_particle!(popl, state): population.jl:103-113 + setr! of the newborn (collisions.jl:104,118,128,132)
-__device__ __forceinline__ void add_particle(const AdvanceParams& P, int sp, Vec3 x, Vec3 p, double w, double t, double s, uint64_t uid) {
+__device__ __noinline__ void add_particle(const AdvanceParams& P, int sp, Vec3 x, Vec3 p, double w, double t, double s, uint64_t uid) {
     const PopView& Q = P.pop[sp];
     if (!Q.present) return;
     double eng = kinenergy_rt(sp, p);
@@ -65,7 +65,7 @@ __device__ __forceinline__ double own_ratebound(const AdvanceParams& P, const Sm
 
 // setr!: collisions.jl:63-74
 template <int SP>
-__device__ __forceinline__ double setr(const AdvanceParams& P, const SmemTable& S, Vec3 p) {
+__device__ __noinline__ double setr(const AdvanceParams& P, const SmemTable& S, Vec3 p) {
     double eng = kinenergy<SP>(p);
     if (eng < P.pop[SP].energy_cut) return 0.0;
     return own_ratebound<SP>(P, S, eng);

@@ -26,6 +26,7 @@ constexpr int WF_WARPS = WF_THREADS / 32;
 
 enum { WS_LOAD = 0, WS_STEP, WS_COULOMB, WS_RBEB, WS_IONFIN, WS_OTHER, WS_IDLE, WS_NCLASS };
 static_assert(WS_IDLE == 6 && WF_WARPS == 8, "the lane-parallel scheduler assumes 6 work classes x 8 warps");
+constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the shared-memory cumulative-rate table
 constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
 constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 
@@ -33,7 +34,8 @@ constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 enum { WD_X0 = 0, WD_X1, WD_X2, WD_P0, WD_P1, WD_P2, WD_T, WD_S, WD_R, WD_TREM, WD_ENG, WD_SCR, WD_NCOL };
 
 struct WfPool {
-    double* d;              // [WD_NCOL][WF_THREADS]
+    double* d;              // [WD_NCOL][np]
+    int np;                 // slots in the pool (column stride)
     unsigned long long* uid;
     long long* row;
     uint32_t *idx, *cblock, *c2, *c3, *state;   // state: class | flags | (proc index << 16)
@@ -56,12 +58,12 @@ __device__ __forceinline__ void wf_store_rng(const WfPool& S, int it, const Rng&
     S.idx[it] = rng.idx; S.cblock[it] = rng.cblock; S.c2[it] = rng.c2; S.c3[it] = rng.c3;
 }
 __device__ __forceinline__ Vec3 wf_get3(const WfPool& S, int c0, int it) {
-    return {S.d[(c0 + 0) * WF_THREADS + it], S.d[(c0 + 1) * WF_THREADS + it], S.d[(c0 + 2) * WF_THREADS + it]};
+    return {S.d[(c0 + 0) * S.np + it], S.d[(c0 + 1) * S.np + it], S.d[(c0 + 2) * S.np + it]};
 }
 __device__ __forceinline__ void wf_put3(const WfPool& S, int c0, int it, Vec3 v) {
-    S.d[(c0 + 0) * WF_THREADS + it] = v.x; S.d[(c0 + 1) * WF_THREADS + it] = v.y; S.d[(c0 + 2) * WF_THREADS + it] = v.z;
+    S.d[(c0 + 0) * S.np + it] = v.x; S.d[(c0 + 1) * S.np + it] = v.y; S.d[(c0 + 2) * S.np + it] = v.z;
 }
-#define WFD(col, it) S.d[(col) * WF_THREADS + (it)]
+#define WFD(col, it) S.d[(col) * S.np + (it)]
 
 // after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP
 template <int SP>
@@ -81,14 +83,44 @@ __device__ __forceinline__ void wf_after_collision(const AdvanceParams& P, const
 // to the reference's sequential scan on the per-process table, so the selected process is always identical.
 template <int TK, bool FAST>
 __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, const Pre& pre,
+                                         double xi0, double r, bool& rate_bound_violated);
+
+// cold paths of the selection (tables that do not fit the fast layout; exact sequential scan inside the guard band)
+template <int TK>
+__device__ __noinline__ int wf_select_generic(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, Pre pre,
+                                              double xi0, double r, int* rbv) {
+    bool b;
+    int j = wf_select<TK, false>(P, T, cum, pre, xi0, r, b);
+    *rbv = b ? 1 : 0;
+    return j;
+}
+template <int TK>
+__device__ __noinline__ int wf_select_sequential(const TableView& T, Pre pre, double xi0, int* rbv) {
+    const int np = T.nprocs;
+    double xi = xi0;
+    int jsel = -1;
+    for (int j = 0; j < np; j++) {
+        double nu = (TK == 0) ? chebsum(T.rate + (size_t)T.order * (j + (size_t)np * pre.i), pre, T.order)
+                              : linear_rate(T.rate, np, j, pre);
+        if (nu > xi) { jsel = j; break; }
+        xi -= nu;
+    }
+    *rbv = (jsel < 0 && !(xi >= 0)) ? 1 : 0;
+    return jsel;
+}
+
+template <int TK, bool FAST>
+__device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, const Pre& pre,
                                          double xi0, double r, bool& rate_bound_violated) {
     const int np = T.nprocs;
     int jsel = -1;
     bool nearb = false;
     const double guard = 1e-9 * r;
     if (TK == 0 && FAST) {
-        // shared-memory layout [interval][m][16] (order 3, <= 16 processes, padded with -inf): two processes per LDS.128
-        const double2* c0 = reinterpret_cast<const double2*>(cum + 48 * pre.i);
+        // shared-memory layout [interval][m][16] (order 3, <= 16 processes, padded with -inf): two processes per LDS.128.
+        // Interval stride WF_CUM_STRIDE = 50 doubles (400 B = 4 banks mod 32): lanes in different energy intervals hit
+        // different banks (a 384-B stride put every interval on the same banks: 14e9 conflict wavefronts in ncu).
+        const double2* c0 = reinterpret_cast<const double2*>(cum + WF_CUM_STRIDE * pre.i);
 #pragma unroll
         for (int j2 = 0; j2 < 8; j2++) {
             if (2 * j2 >= np) break;
@@ -128,17 +160,236 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
     }
     rate_bound_violated = false;
     if (nearb) {   // exact sequential scan of the reference on the per-process rates (global memory; ~never taken)
-        double xi = xi0;
-        jsel = -1;
-        for (int j = 0; j < np; j++) {
-            double nu = (TK == 0) ? chebsum(T.rate + (size_t)T.order * (j + (size_t)np * pre.i), pre, T.order)
-                                  : linear_rate(T.rate, np, j, pre);
-            if (nu > xi) { jsel = j; break; }
-            xi -= nu;
-        }
-        rate_bound_violated = jsel < 0 && !(xi >= 0);
+        int rbv = 0;
+        jsel = wf_select_sequential<TK>(T, pre, xi0, &rbv);
+        rate_bound_violated = rbv != 0;
     }
     return jsel;
+}
+
+// One work unit of slot `it` (state word `sw`).  Shared by the barrier-synchronous kernel (k_advance_wf) and the
+// queue-driven kernel (k_advance_aq).  `ldmask` = lanes of this warp that execute a LOAD unit right now (they share one
+// atomic on the global row counter).
+template <int SP, int TK, bool FIRST, bool CB>
+__device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const TableView& T, const PopView& Q, const WfPool& S,
+                                                const SmemTable& TS, const double* tcum, const bool fastsel, const RngCtx rc,
+                                                const double cut, const int it, const uint32_t sw, const unsigned ldmask,
+                                                const int lane, const unsigned ltmask, unsigned long long* row_counter,
+                                                const long long i0, const long long i1, unsigned long long& nsub) {
+    const int cls = (int)(sw & 0xffu);
+    switch (cls) {
+    // ------------------------------------------------------------------------------------------
+    case WS_LOAD: {   // write back the finished particle of this slot (if any), fetch the next row
+        if (sw & WF_VALID) {
+            long long i = S.row[it];
+            Q.col[COL_X0][i] = WFD(WD_X0, it); Q.col[COL_X1][i] = WFD(WD_X1, it); Q.col[COL_X2][i] = WFD(WD_X2, it);
+            Q.col[COL_P0][i] = WFD(WD_P0, it); Q.col[COL_P1][i] = WFD(WD_P1, it); Q.col[COL_P2][i] = WFD(WD_P2, it);
+            Q.col[COL_T][i] = WFD(WD_T, it); Q.col[COL_S][i] = WFD(WD_S, it); Q.col[COL_R][i] = WFD(WD_R, it);
+            if (sw & WF_DEAD) Q.active[i] = 0;
+        }
+        int leader = __ffs(ldmask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(row_counter, (unsigned long long)__popc(ldmask));
+        base = __shfl_sync(ldmask, base, leader);
+        long long i = i0 + (long long)base + __popc(ldmask & ltmask);
+        if (i >= i1) { S.state[it] = WS_IDLE; break; }
+        if (!Q.active[i]) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (mixed_population.jl:63)
+        Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
+        Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+        double t = Q.col[COL_T][i];
+        wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
+        WFD(WD_T, it) = t; WFD(WD_S, it) = Q.col[COL_S][i];
+        WFD(WD_R, it) = FIRST ? setr<SP>(P, TS, p) : Q.col[COL_R][i];     // advance_init!  mixed_population.jl:97-110
+        WFD(WD_TREM, it) = P.tfinal - t;                                   // :65
+        S.uid[it] = Q.uid[i]; S.row[it] = i;
+        S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
+        S.state[it] = WS_STEP | WF_VALID;
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_STEP: {   // one iteration of mixed_population.jl:66-87 up to the process selection
+        double trem = WFD(WD_TREM, it);
+        if (!(trem > DBL_EPS)) { S.state[it] = WS_LOAD | WF_VALID; break; }       // :66
+        double s = WFD(WD_S, it), r = WFD(WD_R, it), t = WFD(WD_T, it);
+        Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
+        double tnext = s / r;                           // :67
+        bool collides = trem > tnext;                   // :68
+        double dt = collides ? tnext : trem;
+        if (!collides) s -= dt * r;                     // :74
+        Vec3 xo = x, po = p;
+        double to = t;
+        push<SP>(P, x, p, t, dt);                       // :77
+        trem -= dt;                                     // :86
+        nsub++;
+        // a free flight ends the step (trem - dt == 0); after a collision the loop test is re-evaluated
+        uint32_t next = collides ? (WS_STEP | WF_VALID) : (WS_LOAD | WF_VALID);
+        bool act = true;
+        Rng rng;
+        bool rng_loaded = false;
+        if (CB) {                                       // onadvance(WallCallback)  callback.jl:167-184
+            for (int k = 0; k < P.cb.nwalls; k++) {
+                const ptl_wall_desc& wd = P.cb.wall[k];
+                if (wd.species != SP) continue;
+                double xoc = wd.coord == 0 ? xo.x : (wd.coord == 1 ? xo.y : xo.z);
+                double xnc = wd.coord == 0 ? x.x : (wd.coord == 1 ? x.y : x.z);
+                if (xoc < wd.v && wd.v < xnc) {
+                    double f = (wd.v - xoc) / (xnc - xoc);
+                    if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
+                    rng.skip();   // lincomb's 4-arg constructor draws (and discards) an s  (electron.jl:127-132)
+                    const WallBuf& W = P.wall[k];
+                    double wgt = Q.col[COL_W][S.row[it]];
+                    unsigned long long slot = atomicAdd(W.n, 1ULL);
+                    if ((long long)slot < W.capacity) {
+                        W.col[0][slot] = x.x * f + xo.x * (1 - f); W.col[1][slot] = x.y * f + xo.y * (1 - f); W.col[2][slot] = x.z * f + xo.z * (1 - f);
+                        W.col[3][slot] = p.x * f + po.x * (1 - f); W.col[4][slot] = p.y * f + po.y * (1 - f); W.col[5][slot] = p.z * f + po.z * (1 - f);
+                        W.col[6][slot] = wgt * f + wgt * (1 - f);
+                        W.col[7][slot] = t * f + to * (1 - f);
+                    } else {
+                        atomicOr(P.flags, PTL_ERR_CAPACITY_OVERFLOW);
+                    }
+                    if (wd.drop) act = false;
+                }
+            }
+        }
+        if (!act) next = WS_LOAD | WF_VALID | WF_DEAD;
+        if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
+            double eng;
+            if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {                     // :148-151
+                Pre pre = (TK == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
+                if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+                if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
+                rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
+                double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;             // :154
+                const int np = T.nprocs;
+                bool rbv;
+                int jsel;                                                                   // :166-180
+                        if (fastsel) {
+                            jsel = wf_select<TK, true>(P, T, tcum, pre, xi, r, rbv);
+                        } else {
+                            int rb2 = 0;
+                            jsel = wf_select_generic<TK>(P, T, tcum, pre, xi, r, &rb2);
+                            rbv = rb2 != 0;
+                        }
+                if (rbv) atomicOr(P.flags, PTL_ERR_RATE_BOUND_VIOLATED);            // :186
+                if (CB && P.cb.count_collisions) atomicAdd(T.counts + (jsel >= 0 ? jsel : np), 1ULL);
+                int kind = jsel >= 0 ? TS.procs[jsel].kind : PTL_PROC_NULL;
+                if (kind == PTL_PROC_NULL) {            // NullOutcome: setr! then s = nextcoll()  (:83-88, :182-196)
+                    // setr! recomputes kinenergy and presample from the same p: reuse them
+                    r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : T.maxrate;
+                    s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                } else {
+                    WFD(WD_ENG, it) = eng;
+                    uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
+                    next = c | WF_VALID | ((uint32_t)jsel << 16);
+                }
+            }
+        }
+        if (rng_loaded) wf_store_rng(S, it, rng);
+        wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
+        WFD(WD_T, it) = t; WFD(WD_S, it) = s; WFD(WD_R, it) = r; WFD(WD_TREM, it) = trem;
+        S.state[it] = next;
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_COULOMB: {   // collide(::RelativisticCoulomb) + apply!(StateChange)
+        Rng rng;
+        wf_load_rng(S, it, rng);
+        Vec3 p = wf_get3(S, WD_P0, it);
+        Outcome o;
+        collide_coulomb<SP>(rng, rc, TS.procs[sw >> 16], p, o);
+        wf_store_rng(S, it, rng);
+        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_RBEB: {   // rejection trials of rbeb.jl:170-196, two per unit
+        Rng rng;
+        wf_load_rng(S, it, rng);
+        double eng = WFD(WD_ENG, it);
+        double B = TS.procs[sw >> 16].par[0];
+        RbebConsts k = rbeb_consts(eng, B);
+        double w;
+        bool acc = false;
+#pragma unroll 1
+        for (int q = 0; q < 2 && !acc; q++) {
+            double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+            double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+            acc = rbeb_trial(k, u, u2, w);
+        }
+        wf_store_rng(S, it, rng);
+        if (acc) {
+            WFD(WD_SCR, it) = B * w;      // E2
+            S.state[it] = WS_IONFIN | WF_VALID | (sw & 0xffff0000u);
+        }
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_IONFIN: {   // rbeb.jl:58-80 after the sampler: kinematics, apply!(NewParticle), birth
+        Rng rng;
+        wf_load_rng(S, it, rng);
+        double eng = WFD(WD_ENG, it), E2 = WFD(WD_SCR, it);
+        double B = TS.procs[sw >> 16].par[0];
+        double E1 = eng - E2 - B;
+        if (!(E2 < E1)) atomicOr(P.flags, PTL_ERR_SAMPLER_INVARIANT);   // @assert E2 < E1  rbeb.jl:63
+        Vec3 p = wf_get3(S, WD_P0, it);
+        Outcome o;
+        const double ccut = P.pop[PTL_ELECTRON].present ? P.pop[PTL_ELECTRON].energy_cut : INFINITY;
+        ionization_products(rng, rc, p, eng, E1, E2, o, ccut);
+        wf_store_rng(S, it, rng);
+        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+        if (o.sp2 >= 0) {
+            uint64_t cu[2];
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            long long i = S.row[it];
+            add_particle(P, PTL_ELECTRON, wf_get3(S, WD_X0, it), o.p2, Q.col[COL_W][i], WFD(WD_T, it), o.s2, cu[0]);
+        }
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
+        Rng rng;
+        wf_load_rng(S, it, rng);
+        Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
+        double eng = WFD(WD_ENG, it), t = WFD(WD_T, it);
+        Outcome o;
+        collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
+        wf_store_rng(S, it, rng);
+        long long i = S.row[it];
+        uint64_t cu[2];
+        switch (o.kind) {
+        case OUT_NULL:
+            WFD(WD_R, it) = setr<SP>(P, TS, p);
+            WFD(WD_S, it) = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+            wf_store_rng(S, it, rng);
+            S.state[it] = WS_STEP | WF_VALID;
+            break;
+        case OUT_STATE_CHANGE:
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+            break;
+        case OUT_NEW_PARTICLE:
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            break;
+        case OUT_REMOVE:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            break;
+        case OUT_REPLACE:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            break;
+        case OUT_REPLACE_PAIR:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            add_particle(P, o.sp3, x, o.p3, Q.col[COL_W][i], t, o.s3, cu[1]);
+            break;
+        }
+        break;
+    }
+    default: break;
+    }
 }
 
 template <int SP, int TK, bool FIRST, bool CB>
@@ -149,6 +400,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const 
     const PopView& Q = P.pop[SP];
     // ---- carve shared memory: particle pool, then the rate table ----
     WfPool S;
+    S.np = WF_THREADS;
     unsigned char* ptr = smem_raw;
     S.d = reinterpret_cast<double*>(ptr); ptr += sizeof(double) * WD_NCOL * WF_THREADS;
     S.uid = reinterpret_cast<unsigned long long*>(ptr); ptr += 8 * WF_THREADS;
@@ -164,15 +416,16 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const 
     double* tsm = reinterpret_cast<double*>(smem_raw + WF_POOL_BYTES);
     // table in shared memory: Chebyshev -> cumulative rows + rate bound + process descriptors; linear -> descriptors only
     const bool fastsel = (TK == 0) && T.order == 3 && T.nprocs <= 16;
-    const int nrate = (TK == 0) ? (fastsel ? 48 * (T.k + 1) : T.order * T.nprocs * (T.k + 1)) : 0;
+    const int nrate = (TK == 0) ? (fastsel ? WF_CUM_STRIDE * (T.k + 1) : T.order * T.nprocs * (T.k + 1)) : 0;
     const int nrb = (TK == 0) ? T.order * (T.k + 1) : 0;
     {
         const int nproc_dbl = (T.nprocs * (int)sizeof(ptl_process_desc)) / 8;
         const double* pd = reinterpret_cast<const double*>(T.procs);
         if (fastsel) {
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) {
-                int j = q & 15, m = (q >> 4) % 3, i = q / 48;
-                tsm[q] = j < T.nprocs ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
+                int i = q / WF_CUM_STRIDE, rr = q - i * WF_CUM_STRIDE;
+                int j = rr & 15, m = rr >> 4;
+                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
             }
         } else {
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) tsm[q] = T.cum[q];
@@ -276,214 +529,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const 
         const int cls = (int)(sw & 0xffu);
         const unsigned ldmask = __ballot_sync(0xffffffffu, has && cls == WS_LOAD);
 
-        if (has) {
-            switch (cls) {
-            // ------------------------------------------------------------------------------------------
-            case WS_LOAD: {   // write back the finished particle of this slot (if any), fetch the next row
-                if (sw & WF_VALID) {
-                    long long i = S.row[it];
-                    Q.col[COL_X0][i] = WFD(WD_X0, it); Q.col[COL_X1][i] = WFD(WD_X1, it); Q.col[COL_X2][i] = WFD(WD_X2, it);
-                    Q.col[COL_P0][i] = WFD(WD_P0, it); Q.col[COL_P1][i] = WFD(WD_P1, it); Q.col[COL_P2][i] = WFD(WD_P2, it);
-                    Q.col[COL_T][i] = WFD(WD_T, it); Q.col[COL_S][i] = WFD(WD_S, it); Q.col[COL_R][i] = WFD(WD_R, it);
-                    if (sw & WF_DEAD) Q.active[i] = 0;
-                }
-                int leader = __ffs(ldmask) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(row_counter, (unsigned long long)__popc(ldmask));
-                base = __shfl_sync(ldmask, base, leader);
-                long long i = i0 + (long long)base + __popc(ldmask & ltmask);
-                if (i >= i1) { S.state[it] = WS_IDLE; break; }
-                if (!Q.active[i]) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (mixed_population.jl:63)
-                Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
-                Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
-                double t = Q.col[COL_T][i];
-                wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
-                WFD(WD_T, it) = t; WFD(WD_S, it) = Q.col[COL_S][i];
-                WFD(WD_R, it) = FIRST ? setr<SP>(P, TS, p) : Q.col[COL_R][i];     // advance_init!  mixed_population.jl:97-110
-                WFD(WD_TREM, it) = P.tfinal - t;                                   // :65
-                S.uid[it] = Q.uid[i]; S.row[it] = i;
-                S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
-                S.state[it] = WS_STEP | WF_VALID;
-                break;
-            }
-            // ------------------------------------------------------------------------------------------
-            case WS_STEP: {   // one iteration of mixed_population.jl:66-87 up to the process selection
-                double trem = WFD(WD_TREM, it);
-                if (!(trem > DBL_EPS)) { S.state[it] = WS_LOAD | WF_VALID; break; }       // :66
-                double s = WFD(WD_S, it), r = WFD(WD_R, it), t = WFD(WD_T, it);
-                Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
-                double tnext = s / r;                           // :67
-                bool collides = trem > tnext;                   // :68
-                double dt = collides ? tnext : trem;
-                if (!collides) s -= dt * r;                     // :74
-                Vec3 xo = x, po = p;
-                double to = t;
-                push<SP>(P, x, p, t, dt);                       // :77
-                trem -= dt;                                     // :86
-                nsub++;
-                // a free flight ends the step (trem - dt == 0); after a collision the loop test is re-evaluated
-                uint32_t next = collides ? (WS_STEP | WF_VALID) : (WS_LOAD | WF_VALID);
-                bool act = true;
-                Rng rng;
-                bool rng_loaded = false;
-                if (CB) {                                       // onadvance(WallCallback)  callback.jl:167-184
-                    for (int k = 0; k < P.cb.nwalls; k++) {
-                        const ptl_wall_desc& wd = P.cb.wall[k];
-                        if (wd.species != SP) continue;
-                        double xoc = wd.coord == 0 ? xo.x : (wd.coord == 1 ? xo.y : xo.z);
-                        double xnc = wd.coord == 0 ? x.x : (wd.coord == 1 ? x.y : x.z);
-                        if (xoc < wd.v && wd.v < xnc) {
-                            double f = (wd.v - xoc) / (xnc - xoc);
-                            if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
-                            rng.skip();   // lincomb's 4-arg constructor draws (and discards) an s  (electron.jl:127-132)
-                            const WallBuf& W = P.wall[k];
-                            double wgt = Q.col[COL_W][S.row[it]];
-                            unsigned long long slot = atomicAdd(W.n, 1ULL);
-                            if ((long long)slot < W.capacity) {
-                                W.col[0][slot] = x.x * f + xo.x * (1 - f); W.col[1][slot] = x.y * f + xo.y * (1 - f); W.col[2][slot] = x.z * f + xo.z * (1 - f);
-                                W.col[3][slot] = p.x * f + po.x * (1 - f); W.col[4][slot] = p.y * f + po.y * (1 - f); W.col[5][slot] = p.z * f + po.z * (1 - f);
-                                W.col[6][slot] = wgt * f + wgt * (1 - f);
-                                W.col[7][slot] = t * f + to * (1 - f);
-                            } else {
-                                atomicOr(P.flags, PTL_ERR_CAPACITY_OVERFLOW);
-                            }
-                            if (wd.drop) act = false;
-                        }
-                    }
-                }
-                if (!act) next = WS_LOAD | WF_VALID | WF_DEAD;
-                if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
-                    double eng;
-                    if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {                     // :148-151
-                        Pre pre = (TK == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
-                        if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
-                        if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
-                        rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
-                        double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;             // :154
-                        const int np = T.nprocs;
-                        bool rbv;
-                        int jsel = fastsel ? wf_select<TK, true>(P, T, tcum, pre, xi, r, rbv) : wf_select<TK, false>(P, T, tcum, pre, xi, r, rbv);   // :166-180
-                        if (rbv) atomicOr(P.flags, PTL_ERR_RATE_BOUND_VIOLATED);            // :186
-                        if (CB && P.cb.count_collisions) atomicAdd(T.counts + (jsel >= 0 ? jsel : np), 1ULL);
-                        int kind = jsel >= 0 ? TS.procs[jsel].kind : PTL_PROC_NULL;
-                        if (kind == PTL_PROC_NULL) {            // NullOutcome: setr! then s = nextcoll()  (:83-88, :182-196)
-                            // setr! recomputes kinenergy and presample from the same p: reuse them
-                            r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : T.maxrate;
-                            s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
-                        } else {
-                            WFD(WD_ENG, it) = eng;
-                            uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
-                            next = c | WF_VALID | ((uint32_t)jsel << 16);
-                        }
-                    }
-                }
-                if (rng_loaded) wf_store_rng(S, it, rng);
-                wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
-                WFD(WD_T, it) = t; WFD(WD_S, it) = s; WFD(WD_R, it) = r; WFD(WD_TREM, it) = trem;
-                S.state[it] = next;
-                break;
-            }
-            // ------------------------------------------------------------------------------------------
-            case WS_COULOMB: {   // collide(::RelativisticCoulomb) + apply!(StateChange)
-                Rng rng;
-                wf_load_rng(S, it, rng);
-                Vec3 p = wf_get3(S, WD_P0, it);
-                Outcome o;
-                collide_coulomb<SP>(rng, rc, TS.procs[sw >> 16], p, o);
-                wf_store_rng(S, it, rng);
-                wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
-                break;
-            }
-            // ------------------------------------------------------------------------------------------
-            case WS_RBEB: {   // rejection trials of rbeb.jl:170-196, two per unit
-                Rng rng;
-                wf_load_rng(S, it, rng);
-                double eng = WFD(WD_ENG, it);
-                double B = TS.procs[sw >> 16].par[0];
-                RbebConsts k = rbeb_consts(eng, B);
-                double w;
-                bool acc = false;
-#pragma unroll 1
-                for (int q = 0; q < 2 && !acc; q++) {
-                    double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
-                    double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
-                    acc = rbeb_trial(k, u, u2, w);
-                }
-                wf_store_rng(S, it, rng);
-                if (acc) {
-                    WFD(WD_SCR, it) = B * w;      // E2
-                    S.state[it] = WS_IONFIN | WF_VALID | (sw & 0xffff0000u);
-                }
-                break;
-            }
-            // ------------------------------------------------------------------------------------------
-            case WS_IONFIN: {   // rbeb.jl:58-80 after the sampler: kinematics, apply!(NewParticle), birth
-                Rng rng;
-                wf_load_rng(S, it, rng);
-                double eng = WFD(WD_ENG, it), E2 = WFD(WD_SCR, it);
-                double B = TS.procs[sw >> 16].par[0];
-                double E1 = eng - E2 - B;
-                if (!(E2 < E1)) atomicOr(P.flags, PTL_ERR_SAMPLER_INVARIANT);   // @assert E2 < E1  rbeb.jl:63
-                Vec3 p = wf_get3(S, WD_P0, it);
-                Outcome o;
-                ionization_products(rng, rc, p, eng, E1, E2, o);
-                wf_store_rng(S, it, rng);
-                wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
-                // add_particle! cut test first (population.jl:105): most secondaries are far below the cut
-                if (P.pop[PTL_ELECTRON].present && E2 > P.pop[PTL_ELECTRON].energy_cut * 0.9) {
-                    uint64_t cu[2];
-                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-                    long long i = S.row[it];
-                    add_particle(P, PTL_ELECTRON, wf_get3(S, WD_X0, it), o.p2, Q.col[COL_W][i], WFD(WD_T, it), o.s2, cu[0]);
-                }
-                break;
-            }
-            // ------------------------------------------------------------------------------------------
-            case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
-                Rng rng;
-                wf_load_rng(S, it, rng);
-                Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
-                double eng = WFD(WD_ENG, it), t = WFD(WD_T, it);
-                Outcome o;
-                collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
-                wf_store_rng(S, it, rng);
-                long long i = S.row[it];
-                uint64_t cu[2];
-                switch (o.kind) {
-                case OUT_NULL:
-                    WFD(WD_R, it) = setr<SP>(P, TS, p);
-                    WFD(WD_S, it) = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
-                    wf_store_rng(S, it, rng);
-                    S.state[it] = WS_STEP | WF_VALID;
-                    break;
-                case OUT_STATE_CHANGE:
-                    wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
-                    break;
-                case OUT_NEW_PARTICLE:
-                    wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
-                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-                    break;
-                case OUT_REMOVE:
-                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-                    break;
-                case OUT_REPLACE:
-                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-                    break;
-                case OUT_REPLACE_PAIR:
-                    S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-                    child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-                    add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-                    add_particle(P, o.sp3, x, o.p3, Q.col[COL_W][i], t, o.s3, cu[1]);
-                    break;
-                }
-                break;
-            }
-            default: break;
-            }
-        }
+        if (has) wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, ldmask, lane, ltmask, row_counter, i0, i1, nsub);
         __syncthreads();
     }
 

@@ -11,6 +11,7 @@
 
 #include "ptl_advance.cuh"
 #include "ptl_advance_wf.cuh"
+#include "ptl_advance_aq.cuh"
 #include "ptl_store.cuh"
 
 using namespace ptl;
@@ -23,7 +24,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
     int flags;
     int _pad;
     unsigned long long substeps, births, tile_counter, total, nmoves;
-    unsigned long long pop_n[16];
+    unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[DIAG_NVAL];
 };
@@ -91,6 +92,7 @@ struct ptl_context {
     int partial_blocks = 0;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    int kernel_mode = 0;               // PTL_KERNEL=aq selects the queue-driven lepton kernel, =wf the barrier-synchronous one
     long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -214,7 +216,7 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     auto kern = k_advance_wf<SP, TK, FIRST, CB>;
     const TableView& TV = A.tab[SP];
     size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
-    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? 48 : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
     (void)table_smem;
     size_t smem = wf_pool_bytes() + tsm + 32;
     static bool configured = false;
@@ -240,8 +242,43 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     return 0;
 }
 
+// queue-driven variant: autonomous warps, per-class ring buffers in shared memory
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_aq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1) {
+    auto kern = k_advance_aq<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    size_t smem = AQ_POOL_BYTES + tsm + 32;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        configured = true;
+    }
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, AQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long rows = i1 - i0;
+    long long want = (rows + AQ_SLOTS - 1) / AQ_SLOTS;
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, AQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
 template <int SP, bool FIRST, bool CB>
 int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem) {
+    if (ctx->kernel_mode == 1) {
+        if (A.tab[SP].kind == 0) return launch_advance_aq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1);
+        return launch_advance_aq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1);
+    }
     if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem);
     return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem);
 }
@@ -297,6 +334,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     ptl_context* ctx = new ptl_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : 0;
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -495,7 +533,7 @@ EXPORT int32_t ptl_table_eval(ptl_context* ctx, int32_t table, int64_t n, const 
 EXPORT int32_t ptl_population_create(ptl_context* ctx, int32_t species, int64_t capacity, double energy_cut, int32_t table) {
     if (!ctx || species < 0 || species >= PTL_NSPECIES || capacity < 1) return PTL_EINVAL;
     if (table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
-    if (ctx->pops.size() >= 16) return PTL_ENOMEM;
+    if (ctx->pops.size() >= 64) return PTL_ENOMEM;
     Pop P;
     size_t colb = align256(sizeof(double) * (size_t)capacity);
     size_t actb = align256((size_t)capacity);
@@ -870,6 +908,19 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
     if (has_cb) A.cb = *cb;
     A.has_cb = has_cb ? 1 : 0;
     A.tfinal = tfinal;
+    // canonicalise: a HomogeneousField of zeros is no field (e + v x 0 == e), and a lone uniform E is the hot path
+    for (int k = 0; k < A.pusher.nforcings; k++) {
+        ptl_forcing_desc& f = A.pusher.forcing[k];
+        if (f.kind == PTL_FORCE_EM && f.b.kind == PTL_FIELD_HOMOGENEOUS && f.b.par[0] == 0 && f.b.par[1] == 0 && f.b.par[2] == 0)
+            f.b.kind = PTL_FIELD_ZERO;
+    }
+    A.fast_force = 0;
+    if (A.pusher.kind == PTL_PUSHER_RK2 && A.pusher.nforcings == 1 && A.pusher.forcing[0].kind == PTL_FORCE_EM &&
+        A.pusher.forcing[0].species_mask == 0 && A.pusher.forcing[0].e.kind == PTL_FIELD_HOMOGENEOUS &&
+        A.pusher.forcing[0].b.kind == PTL_FIELD_ZERO) {
+        A.fast_force = 1;
+        for (int c = 0; c < 3; c++) A.fastE[c] = A.pusher.forcing[0].e.par[c] * CO_E;
+    }
     memset(&ctx->stats, 0, sizeof(ctx->stats));
     CK(cudaMemsetAsync(&ctx->d_sc->substeps, 0, 2 * sizeof(unsigned long long), ctx->stream));   // substeps, births
     for (int pi : M.pops) ctx->pops[pi].iup = 0;   // advance_init!: iup = 1  (mixed_population.jl:101)

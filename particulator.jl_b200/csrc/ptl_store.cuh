@@ -249,6 +249,8 @@ __global__ void k_split(PopView Q, long long n, double pmean, uint32_t step, uin
         double u = rng.u(step, seed_lo, seed_hi);
         double pk = exp(-pmean), cdf = pk;   // Poisson(p) by sequential inversion
         while (u > cdf && k < 1000) { k++; pk *= pmean / k; cdf += pk; }
+        Vec3 pp = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+        if (!(kinenergy_rt(Q.species, pp) > Q.energy_cut)) k = 0;   // add_particle! refuses copies at or below the cut (population.jl:105)
     }
     // warp-aggregated append of all copies
     int lane = threadIdx.x & 31;
@@ -262,13 +264,10 @@ __global__ void k_split(PopView Q, long long n, double pmean, uint32_t step, uin
     if (lane == 31 && tot) base = atomicAdd(Q.n, (unsigned long long)tot);
     base = __shfl_sync(0xffffffffu, base, 31);
     if (!act || k == 0) return;
-    Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
-    bool keep = kinenergy_rt(Q.species, p) > Q.energy_cut;   // add_particle! cut (population.jl:105)
     uint64_t uid = Q.uid[i];
     for (int c = 0; c < k; c++) {
         long long slot = (long long)base + (incl - k) + c;
         if (slot >= Q.capacity) { atomicOr(flags, PTL_ERR_CAPACITY_OVERFLOW); break; }
-        if (!keep) { Q.active[slot] = 0; continue; }   // reserved row stays an inactive hole until the next repack!
         uint64_t cu[2];
         child_uids(uid ^ ((uint64_t)DOM_SPLIT << 32), (uint32_t)c, step, seed_lo, seed_hi, cu);
 #pragma unroll

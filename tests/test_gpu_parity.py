@@ -327,3 +327,73 @@ def test_large_population_properties(gctx, air_tables):
     P.repack(el)
     assert np.array_equal(a, el.download(("uid",))["uid"])
     assert gctx.error_flags() == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# population control: roulette! / split!, and the run! loop
+# ---------------------------------------------------------------------------------------------------
+def test_roulette_and_split_replay(gctx, octx, air_tables):
+    st = _random_pop(np.random.default_rng(12), 50000, 0.1)
+    out = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(21, 5)
+        pop = P.Population(ctx, P.ELECTRON, 200000, st, air_tables["electron"], 1e3 * co.eV)
+        P.roulette(0.4, pop)
+        a = pop.download()
+        P.repack(pop)
+        P.split(1.5, pop)
+        n_split = len(pop)
+        b = pop.download()
+        P.repack(pop)
+        out.append((a, n_split, b, P.weight(pop), len(pop)))
+    (ag, ng, bg, wg, lg), (ao, no, bo, wo, lo) = out
+    for k in ag:
+        assert np.array_equal(ag[k], ao[k]), k                 # roulette!: same survivors, same weights (w / p)
+    kept = ag["active"].sum() / st["active"].sum()
+    assert abs(kept - 0.4) < 0.02
+    assert ng == no and lg == lo
+    assert wg == pytest.approx(wo, rel=1e-12)
+    # split!: copies carry w / (1 + p); total weight is conserved in expectation
+    assert sorted(bg["uid"].tolist()) == sorted(bo["uid"].tolist())
+    # (copies of particles at or below the energy cut are refused by add_particle!, population.jl:105)
+    alive = ag["active"] == 1
+    above = P.kinenergy(P.ELECTRON, ag["p"]) > 1e3 * co.eV
+    w_expect = (ag["w"][alive] * (1 / 2.5 + above[alive] * 1.5 / 2.5)).sum()
+    assert abs(wg / w_expect - 1) < 0.02
+
+
+def test_run_loop_observables_agree(gctx, octx, air_tables):
+    """run! for 12 steps (advance! + droplow! each step): counts, mean energy, centroid and the energy spectrum of the
+    CUDA path and of the oracle agree (same uid-keyed streams => almost particle-identical histories)."""
+    res = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(33, 0)
+        mp, el, ph, po = make_world(ctx, air_tables, 4000, 0, 0, cap=60000, seed=13, emin=5e5, emax=2e7)
+        P.run(mp, default_pusher(), 12 * DT, DT, P.VoidCallback(), output_dt=None, verbosity=0)
+        d = el.download()
+        res.append((len(el), len(ph), len(po), P.meanenergy(el), P.spread(el), P.kinenergy(P.ELECTRON, d["p"])))
+    (neg, npg, nposg, meg, spg, eg), (neo, npo_, nposo, meo, spo, eo) = res
+    assert abs(neg - neo) <= 0.01 * neo + 5
+    assert abs(npg - npo_) <= 0.05 * npo_ + 5
+    assert meg == pytest.approx(meo, rel=5e-3)
+    np.testing.assert_allclose(spg[0], spo[0], rtol=5e-3, atol=1e-4)
+    from scipy import stats
+    assert stats.ks_2samp(eg, eo).pvalue > 0.01
+
+
+def test_statistical_agreement_over_seeds(gctx, octx, air_tables):
+    """Statistical tier: independent seeds on each side — avalanche multiplication, mean energy and drift of a
+    1 MeV electron swarm after 8 steps agree within 3 sigma of the seed-to-seed scatter."""
+    def observe(ctx, seed):
+        ctx.set_rng(seed, 0)
+        mp, el, ph, po = make_world(ctx, air_tables, 1500, 0, 0, cap=30000, seed=seed, espec=1e6)
+        P.run(mp, default_pusher(), 8 * DT, DT, P.VoidCallback(), output_dt=None, verbosity=0)
+        d = el.download()
+        e = P.kinenergy(P.ELECTRON, d["p"])
+        hi = e > 1e5 * co.eV
+        return [len(el) / 1500.0, float(e[hi].mean() / co.eV), float(d["x"][hi, 2].mean())]
+    g = np.array([observe(gctx, 100 + s) for s in range(6)])
+    o = np.array([observe(octx, 200 + s) for s in range(6)])
+    for k in range(3):
+        sigma = np.sqrt(g[:, k].var(ddof=1) / 6 + o[:, k].var(ddof=1) / 6)
+        assert abs(g[:, k].mean() - o[:, k].mean()) <= 3 * sigma + 1e-12, (k, g[:, k].mean(), o[:, k].mean(), sigma)
