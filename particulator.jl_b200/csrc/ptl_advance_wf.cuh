@@ -212,7 +212,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         if (!(trem > DBL_EPS)) { S.state[it] = WS_LOAD | WF_VALID; break; }       // :66
         double s = WFD(WD_S, it), r = WFD(WD_R, it), t = WFD(WD_T, it);
         Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
-        double tnext = s / r;                           // :67
+        double tnext = r == 0.0 ? INFINITY : s * frcp(r);   // :67  (r == 0 -> Inf -> free flight)
         bool collides = trem > tnext;                   // :68
         double dt = collides ? tnext : trem;
         if (!collides) s -= dt * r;                     // :74
