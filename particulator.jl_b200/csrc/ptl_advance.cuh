@@ -73,7 +73,10 @@ __device__ __noinline__ double setr(const AdvanceParams& P, const SmemTable& S, 
 
 template <int SP, bool FIRST, bool CB>
 __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
-                                                         unsigned long long* tile_counter) {
+                                                         unsigned long long* tile_counter, const long long* __restrict__ rows,
+                                                         const unsigned long long* __restrict__ nrows) {
+    // index-list mode: process rows[0 .. *nrows) (the particles the streaming kernel deferred) instead of [i0, i1)
+    if (rows != nullptr) { i0 = 0; i1 = (long long)*nrows; }
     extern __shared__ double smem[];
     const TableView& T = P.tab[SP];
     const PopView& Q = P.pop[SP];
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
         if (base >= i1) break;
         long long i = base + lane;
         if (i >= i1) continue;
+        if (rows != nullptr) i = rows[i];
         if (!Q.active[i]) continue;    // l.active || continue   mixed_population.jl:63
 
         Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
@@ -224,6 +228,105 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
     if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+}
+
+// K1s: streaming fast path for species with kappa << 1 (photons: mean free path of metres vs c*dt = 7.5 mm).
+// A particle whose next event lies beyond tfinal does exactly ONE sub-step of the reference loop
+// (mixed_population.jl:66-87 with collides == false): s -= trem*r, one push, t += trem.  That is pure streaming:
+// two particles per thread, 128-bit loads of nine columns (+ active), stores of only the columns that change
+// (x, t, s; r when advance_init! changed it).  Particles that do collide within dt (~1 %) are left untouched and
+// appended to an index list which the general kernel processes afterwards.
+constexpr int STREAM_THREADS = 256;
+
+template <int SP, bool FIRST>
+__global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                                  long long* __restrict__ slow_rows, unsigned long long* slow_count) {
+    extern __shared__ double smem[];
+    const TableView& T = P.tab[SP];
+    const PopView& Q = P.pop[SP];
+    SmemTable S;
+    S.rate = nullptr; S.procs = nullptr;
+    if (T.kind == 0) {
+        int nrb = T.order * (T.k + 1);
+        for (int q = threadIdx.x; q < nrb; q += blockDim.x) smem[q] = T.ratebound[q];
+        S.ratebound = smem;
+    } else {
+        S.ratebound = nullptr;
+    }
+    __syncthreads();
+    unsigned long long nsub = 0;
+    const long long npairs = (i1 - i0 + 1) / 2;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < npairs; q += (long long)gridDim.x * blockDim.x) {
+        const long long i = i0 + 2 * q;          // i0 is even (rows of a pass start at 0 or at an even boundary, see launcher)
+        const bool two = i + 1 < i1;
+        double2 c[9];
+        unsigned char a0, a1 = 0;
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const int col = k < 6 ? k : k + 1;      // x0..p2, t, s, r  (w is not needed)
+                c[k] = *reinterpret_cast<const double2*>(Q.col[col] + i);
+            }
+            uchar2 aa = *reinterpret_cast<const uchar2*>(Q.active + i);
+            a0 = aa.x; a1 = aa.y;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const int col = k < 6 ? k : k + 1;
+                c[k] = make_double2(Q.col[col][i], 0.0);
+            }
+            a0 = Q.active[i];
+        }
+        double xs[2][3], ts[2], ss[2], rs[2];
+        bool wr[2] = {false, false}, wr_r[2] = {false, false};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const bool act = h == 0 ? (a0 != 0) : (two && a1 != 0);
+            Vec3 x = {h ? c[0].y : c[0].x, h ? c[1].y : c[1].x, h ? c[2].y : c[2].x};
+            Vec3 p = {h ? c[3].y : c[3].x, h ? c[4].y : c[4].x, h ? c[5].y : c[5].x};
+            double t = h ? c[6].y : c[6].x, s = h ? c[7].y : c[7].x, r0 = h ? c[8].y : c[8].x;
+            if (!act) continue;
+            double r = FIRST ? setr<SP>(P, S, p) : r0;           // advance_init!
+            double trem = P.tfinal - t;
+            if (!(trem > DBL_EPS)) {                              // nothing to do this step (:66)
+                if (FIRST && r != r0) { wr_r[h] = true; rs[h] = r; }
+                continue;
+            }
+            double tnext = s / r;
+            if (trem > tnext) {                                   // collides within dt: defer to the general kernel
+                unsigned long long k = atomicAdd(slow_count, 1ULL);
+                slow_rows[k] = i + h;
+                continue;
+            }
+            s -= trem * r;                                        // :74
+            push<SP>(P, x, p, t, trem);                           // :77 (photons: p unchanged)
+            nsub++;
+            xs[h][0] = x.x; xs[h][1] = x.y; xs[h][2] = x.z; ts[h] = t; ss[h] = s; rs[h] = r;
+            wr[h] = true;
+            wr_r[h] = FIRST && r != r0;
+            if (SP != PTL_PHOTON) {                               // species whose momentum changes under the pusher
+                Q.col[COL_P0][i + h] = p.x; Q.col[COL_P1][i + h] = p.y; Q.col[COL_P2][i + h] = p.z;
+            }
+        }
+        if (two && wr[0] && wr[1]) {
+            *reinterpret_cast<double2*>(Q.col[COL_X0] + i) = make_double2(xs[0][0], xs[1][0]);
+            *reinterpret_cast<double2*>(Q.col[COL_X1] + i) = make_double2(xs[0][1], xs[1][1]);
+            *reinterpret_cast<double2*>(Q.col[COL_X2] + i) = make_double2(xs[0][2], xs[1][2]);
+            *reinterpret_cast<double2*>(Q.col[COL_T] + i) = make_double2(ts[0], ts[1]);
+            *reinterpret_cast<double2*>(Q.col[COL_S] + i) = make_double2(ss[0], ss[1]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (!wr[h]) continue;
+                Q.col[COL_X0][i + h] = xs[h][0]; Q.col[COL_X1][i + h] = xs[h][1]; Q.col[COL_X2][i + h] = xs[h][2];
+                Q.col[COL_T][i + h] = ts[h]; Q.col[COL_S][i + h] = ss[h];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) if (wr_r[h]) Q.col[COL_R][i + h] = rs[h];
+    }
+    for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
+    if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(P.substeps, nsub);
 }
 
 // init!(mpopl) / advance_init!: setr! on all actives (mixed_population.jl:20-35)

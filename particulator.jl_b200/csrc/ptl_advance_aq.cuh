@@ -96,33 +96,42 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) k_advance_aq(const __grid_const
 
     unsigned idle_polls = 0;
     for (;;) {
-        // ---- lane 0 claims up to 32 items of one class ----
+        // ---- claim up to 32 items of one class ----
+        // lanes 0..5 read the depth of "their" ring in parallel; the deepest ring wins.  A warp prefers to wait a few
+        // hundred ns for a full chunk while other warps still hold items (they are about to push), and only takes a
+        // partial chunk when nobody is processing or the wait budget is spent: keeps ~30 lanes busy per instruction.
         int c_sel = -1;
         unsigned h_sel = 0, k_sel = 0;
-        if (lane == 0) {
-            // two polls: prefer a full chunk; if none shows up take the deepest ring
-            for (int attempt = 0; attempt < 2 && c_sel < 0; attempt++) {
-                int best = -1;
-                unsigned bestn = 0;
+        for (int attempt = 0; attempt < 24; attempt++) {
+            unsigned av = 0;
+            if (lane < AQ_NCLASS) av = A.tail[lane] - A.head[lane];
+            unsigned key = (av << 3) | (unsigned)(7 - lane);          // deepest ring, ties -> lowest class
+            unsigned best = key;
 #pragma unroll
-                for (int c = 0; c < AQ_NCLASS; c++) {
-                    unsigned av = A.tail[c] - A.head[c];
-                    if (av > bestn) { bestn = av; best = c; }
-                }
-                if (best < 0) break;
-                if (bestn < 32 && attempt == 0 && *A.inflight > 0) { __nanosleep(64); continue; }
+            for (int off = 4; off > 0; off >>= 1) { unsigned o = __shfl_xor_sync(0xffffffffu, best, off); best = o > best ? o : best; }
+            best = __shfl_sync(0xffffffffu, best, 0);                  // lanes 0..7 hold the maximum of their group of 8
+            const unsigned bestn = best >> 3;
+            const int bc = 7 - (int)(best & 7u);
+            if (bestn == 0) break;
+            const unsigned infl = *A.inflight;
+            if (bestn < 32 && infl > 0 && attempt < 23) { __nanosleep(40); continue; }
+            int ok = 0;
+            unsigned old = 0, kk = 0;
+            if (lane == 0) {
                 unsigned k = bestn < 32 ? bestn : 32;
                 atomicAdd((unsigned int*)A.inflight, k);
-                unsigned old = A.head[best];
-                unsigned av = A.tail[best] - old;
-                unsigned kk = av < k ? av : k;
-                if (kk > 0 && atomicCAS((unsigned int*)&A.head[best], old, old + kk) == old) {
+                old = A.head[bc];
+                unsigned av2 = A.tail[bc] - old;
+                kk = av2 < k ? av2 : k;
+                if (kk > 0 && atomicCAS((unsigned int*)&A.head[bc], old, old + kk) == old) {
                     if (kk < k) atomicSub((unsigned int*)A.inflight, k - kk);
-                    c_sel = best; h_sel = old; k_sel = kk;
+                    ok = 1;
                 } else {
                     atomicSub((unsigned int*)A.inflight, k);
                 }
             }
+            ok = __shfl_sync(0xffffffffu, ok, 0);
+            if (ok) { c_sel = bc; h_sel = old; k_sel = kk; break; }
         }
         c_sel = __shfl_sync(0xffffffffu, c_sel, 0);
         if (c_sel < 0) {

@@ -23,7 +23,7 @@ namespace {
 struct DeviceScalars {            // one small device block mirrored in pinned host memory
     int flags;
     int _pad;
-    unsigned long long substeps, births, tile_counter, total, nmoves;
+    unsigned long long substeps, births, tile_counter, total, nmoves, slow_count;
     unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[DIAG_NVAL];
@@ -92,6 +92,8 @@ struct ptl_context {
     int partial_blocks = 0;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    long long* d_slow_rows = nullptr;  // rows the streaming photon kernel deferred to the general kernel
+    size_t slow_cap = 0;
     int kernel_mode = 0;               // PTL_KERNEL=aq selects the queue-driven lepton kernel, =wf the barrier-synchronous one
     long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
     bool profiling = false;
@@ -185,7 +187,7 @@ void fill_params(ptl_context* ctx, const MultiPop* mp, AdvanceParams& A) {
 }
 
 template <int SP, bool FIRST, bool CB>
-int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t smem) {
+int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t smem, const long long* rows = nullptr) {
     auto kern = k_advance<SP, FIRST, CB>;
     static bool configured = false;
     static int blocks_per_sm = 1;
@@ -203,7 +205,7 @@ int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0,
     CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
     if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
+    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
     if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
@@ -288,6 +290,34 @@ int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long 
 template <int SP>
 int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
     if constexpr (SP == PTL_PHOTON) {
+        // streaming fast path (kappa << 1): free flights in a bandwidth-tuned kernel, the few colliding rows deferred to
+        // the general kernel through an index list.  Needs an even first row (128-bit loads) and no in-loop callback.
+        if (!cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->kernel_mode != 2) {
+            size_t need = (size_t)(i1 - i0);
+            if (need > ctx->slow_cap) {
+                cudaFree(ctx->d_slow_rows);
+                ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
+                size_t cap = need + need / 4;
+                CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
+                ctx->slow_cap = cap;
+            }
+            CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
+            const TableView& TV = A.tab[SP];
+            size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
+            long long pairs = (i1 - i0 + 1) / 2;
+            long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
+            long long maxgrid = (long long)ctx->sm_count * 8;
+            if (grid > maxgrid) grid = maxgrid;
+            bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+            if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+            if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+            else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+            if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+            LAUNCHED();
+            ctx->stats.launches++;
+            if (first) return launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, ctx->d_slow_rows);
+            return launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, ctx->d_slow_rows);
+        }
         if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem);
         return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem);
     } else {
@@ -334,7 +364,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     ptl_context* ctx = new ptl_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : 0;
+    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : (!strcmp(km, "nostream") ? 2 : 0);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -365,7 +395,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     for (auto& w : ctx->walls) if (w.block) cudaFree(w.block);
     for (int b = 0; b < 2; b++) if (ctx->stage[b]) cudaFree(ctx->stage[b]);
     cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets); cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
-    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp); cudaFree(ctx->d_slow_rows);
     cudaFree(ctx->d_sc);
     cudaFreeHost(ctx->h_sc);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
