@@ -156,6 +156,7 @@ def cpu_leg(P, tables, n_sample, steps, warmup, seed=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_backend import oracle_context, oracle_backend
     ctx = oracle_context()
+    oracle_backend().dll.ora_set_num_threads(int(os.cpu_count() or 1))      # torchrun pins OMP_NUM_THREADS=1
     cores = int(oracle_backend().dll.ora_num_threads())
     mp, el, ph, po = make_world(P, ctx, tables, int(1.5 * n_sample) + 1024, n_sample + 1024, n_sample // 4 + 1024)
     el.upload(synth_electrons_numpy(P, n_sample, seed, 1))
@@ -228,6 +229,9 @@ def main():
         return 0
 
     # ------------------------------------------------------------------------------------------------------------
+    # exactly one JSON line on stdout: everything else this process (or NCCL) prints goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     torch.cuda.set_device(local_rank)
     dist = None
@@ -377,7 +381,7 @@ def main():
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
                 "kappa": substeps_all / max(psteps_all, 1.0), "substeps_per_s": substeps_all / (elapsed_all * 1e-3),
                 "hbm_roofline_frac_whole_step": (ALGO_BYTES_PER_PARTICLE_STEP * value / max(world, 1)) / 1e9 / peak}
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0

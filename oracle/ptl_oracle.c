@@ -1538,6 +1538,15 @@ EXPORT int32_t ora_philox_test(const uint32_t* ctr, const uint32_t* key, uint32_
     philox4x32_10(ctr, key, out);
     return 0;
 }
+/* torchrun exports OMP_NUM_THREADS=1; the timed CPU baseline asks for all host cores explicitly */
+EXPORT int32_t ora_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+    return 0;
+}
 EXPORT int32_t ora_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

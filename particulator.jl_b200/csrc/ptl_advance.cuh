@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
     }
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
-    if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+    if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
 }
 
 // K1s: streaming fast path for species with kappa << 1 (photons: mean free path of metres vs c*dt = 7.5 mm).
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_
         for (int h = 0; h < 2; h++) if (wr_r[h]) Q.col[COL_R][i + h] = rs[h];
     }
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
-    if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(P.substeps, nsub);
+    if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
 }
 
 // init!(mpopl) / advance_init!: setr! on all actives (mixed_population.jl:20-35)

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) k_advance_aq(const __grid_const
     }
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
-    if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+    if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
 }
 
 }  // namespace ptl

@@ -175,7 +175,8 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                                                 const SmemTable& TS, const double* tcum, const bool fastsel, const RngCtx rc,
                                                 const double cut, const int it, const uint32_t sw, const unsigned ldmask,
                                                 const int lane, const unsigned ltmask, unsigned long long* row_counter,
-                                                const long long i0, const long long i1, unsigned long long& nsub) {
+                                                const long long i0, const long long i1, unsigned long long& nsub,
+                                                const long long* __restrict__ rows = nullptr) {
     const int cls = (int)(sw & 0xffu);
     switch (cls) {
     // ------------------------------------------------------------------------------------------
@@ -193,6 +194,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         base = __shfl_sync(ldmask, base, leader);
         long long i = i0 + (long long)base + __popc(ldmask & ltmask);
         if (i >= i1) { S.state[it] = WS_IDLE; break; }
+        if (rows != nullptr) i = rows[i];
         if (!Q.active[i]) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (mixed_population.jl:63)
         Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
         Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
@@ -394,7 +396,9 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
 
 template <int SP, int TK, bool FIRST, bool CB>
 __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
-                                                              unsigned long long* row_counter) {
+                                                              unsigned long long* row_counter, const long long* __restrict__ rows,
+                                                              const unsigned long long* __restrict__ nrows) {
+    if (rows != nullptr) { i0 = 0; i1 = (long long)*nrows; }     // index-list mode (rows deferred by the streaming kernel)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TableView& T = P.tab[SP];
     const PopView& Q = P.pop[SP];
@@ -529,12 +533,12 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const 
         const int cls = (int)(sw & 0xffu);
         const unsigned ldmask = __ballot_sync(0xffffffffu, has && cls == WS_LOAD);
 
-        if (has) wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, ldmask, lane, ltmask, row_counter, i0, i1, nsub);
+        if (has) wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, ldmask, lane, ltmask, row_counter, i0, i1, nsub, rows);
         __syncthreads();
     }
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
-    if (lane == 0 && nsub) atomicAdd(P.substeps, nsub);
+    if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
 }
 
 }  // namespace ptl

@@ -23,7 +23,7 @@ namespace {
 struct DeviceScalars {            // one small device block mirrored in pinned host memory
     int flags;
     int _pad;
-    unsigned long long substeps, births, tile_counter, total, nmoves, slow_count;
+    unsigned long long substeps[PTL_NSPECIES], births, tile_counter, total, nmoves, slow_count;
     unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[DIAG_NVAL];
@@ -44,6 +44,8 @@ struct Pop {
     long long iup = 0;
     int table = -1;
     int slot = -1;                // index into DeviceScalars.pop_n
+    double kappa_est = -1;        // measured sub-steps per row in the last advance (< 0: unknown)
+    long long rows_last = 0;
     bool alive = false;
 };
 
@@ -182,7 +184,7 @@ void fill_params(ptl_context* ctx, const MultiPop* mp, AdvanceParams& A) {
     A.seed_hi = (uint32_t)(ctx->seed >> 32);
     A.step = ctx->step;
     A.flags = &ctx->d_sc->flags;
-    A.substeps = &ctx->d_sc->substeps;
+    A.substeps = ctx->d_sc->substeps;
     A.births = &ctx->d_sc->births;
 }
 
@@ -214,7 +216,7 @@ int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0,
 
 // wavefront variant (collision-dominated species): persistent CTAs, shared-memory particle pool
 template <int SP, int TK, bool FIRST, bool CB>
-int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem) {
+int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows) {
     auto kern = k_advance_wf<SP, TK, FIRST, CB>;
     const TableView& TV = A.tab[SP];
     size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
@@ -229,15 +231,15 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WF_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
         blocks_per_sm = 1;
-    long long rows = i1 - i0;
-    long long want = (rows + WF_THREADS - 1) / WF_THREADS;
+    long long nrow = i1 - i0;
+    long long want = (nrow + WF_THREADS - 1) / WF_THREADS;
     long long grid = (long long)ctx->sm_count * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
     if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
+    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
     if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
@@ -276,62 +278,63 @@ int32_t launch_advance_aq_k(ptl_context* ctx, const AdvanceParams& A, long long 
 }
 
 template <int SP, bool FIRST, bool CB>
-int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem) {
-    if (ctx->kernel_mode == 1) {
+int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows = nullptr) {
+    if (ctx->kernel_mode == 1 && rows == nullptr) {
         if (A.tab[SP].kind == 0) return launch_advance_aq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1);
         return launch_advance_aq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1);
     }
-    if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem);
-    return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem);
+    if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
+    return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
 }
 
-// photons (kappa << 1, HBM-bound) stream through the one-particle-per-lane kernel; collision-dominated species
-// (electrons, positrons, slow electrons) go through the wavefront kernel.  One variant per species is compiled.
+// First-pass kernel choice.  Photons, and any species whose measured kappa (sub-steps per row of the previous advance)
+// is small, are HBM-bound: free flights go through the streaming kernel and only the rows that collide within dt are
+// deferred, through an index list, to the general kernel of the species (one particle per lane for photons, wavefront
+// for leptons).  Collision-dominated populations go straight to the wavefront kernel.
 template <int SP>
-int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
-    if constexpr (SP == PTL_PHOTON) {
-        // streaming fast path (kappa << 1): free flights in a bandwidth-tuned kernel, the few colliding rows deferred to
-        // the general kernel through an index list.  Needs an even first row (128-bit loads) and no in-loop callback.
-        if (!cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->kernel_mode != 2) {
-            size_t need = (size_t)(i1 - i0);
-            if (need > ctx->slow_cap) {
-                cudaFree(ctx->d_slow_rows);
-                ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
-                size_t cap = need + need / 4;
-                CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
-                ctx->slow_cap = cap;
-            }
-            CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
-            const TableView& TV = A.tab[SP];
-            size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
-            long long pairs = (i1 - i0 + 1) / 2;
-            long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
-            long long maxgrid = (long long)ctx->sm_count * 8;
-            if (grid > maxgrid) grid = maxgrid;
-            bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-            if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-            if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-            else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-            if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-            LAUNCHED();
-            ctx->stats.launches++;
-            if (first) return launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, ctx->d_slow_rows);
-            return launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, ctx->d_slow_rows);
+int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem, bool low_kappa) {
+    const long long* rows = nullptr;
+    if ((SP == PTL_PHOTON || low_kappa) && !cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->kernel_mode != 2) {
+        size_t need = (size_t)(i1 - i0);
+        if (need > ctx->slow_cap) {
+            cudaFree(ctx->d_slow_rows);
+            ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
+            size_t cap = need + need / 4;
+            CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
+            ctx->slow_cap = cap;
         }
-        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem);
-        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem);
+        CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
+        const TableView& TV = A.tab[SP];
+        size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
+        long long pairs = (i1 - i0 + 1) / 2;
+        long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
+        long long maxgrid = (long long)ctx->sm_count * 8;
+        if (grid > maxgrid) grid = maxgrid;
+        bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+        if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+        else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+        if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+        LAUNCHED();
+        ctx->stats.launches++;
+        rows = ctx->d_slow_rows;
+        cb = false;
+    }
+    if constexpr (SP == PTL_PHOTON) {
+        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
     } else {
-        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem);
-        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem);
+        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
     }
 }
 
-int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem) {
+int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem, bool low_kappa) {
     switch (species) {
-    case PTL_ELECTRON: return launch_advance_s<PTL_ELECTRON>(ctx, A, i0, i1, first, cb, smem);
-    case PTL_PHOTON: return launch_advance_s<PTL_PHOTON>(ctx, A, i0, i1, first, cb, smem);
-    case PTL_POSITRON: return launch_advance_s<PTL_POSITRON>(ctx, A, i0, i1, first, cb, smem);
-    case PTL_SLOW_ELECTRON: return launch_advance_s<PTL_SLOW_ELECTRON>(ctx, A, i0, i1, first, cb, smem);
+    case PTL_ELECTRON: return launch_advance_s<PTL_ELECTRON>(ctx, A, i0, i1, first, cb, smem, low_kappa);
+    case PTL_PHOTON: return launch_advance_s<PTL_PHOTON>(ctx, A, i0, i1, first, cb, smem, low_kappa);
+    case PTL_POSITRON: return launch_advance_s<PTL_POSITRON>(ctx, A, i0, i1, first, cb, smem, low_kappa);
+    case PTL_SLOW_ELECTRON: return launch_advance_s<PTL_SLOW_ELECTRON>(ctx, A, i0, i1, first, cb, smem, low_kappa);
     }
     return PTL_EINVAL;
 }
@@ -952,8 +955,8 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
         for (int c = 0; c < 3; c++) A.fastE[c] = A.pusher.forcing[0].e.par[c] * CO_E;
     }
     memset(&ctx->stats, 0, sizeof(ctx->stats));
-    CK(cudaMemsetAsync(&ctx->d_sc->substeps, 0, 2 * sizeof(unsigned long long), ctx->stream));   // substeps, births
-    for (int pi : M.pops) ctx->pops[pi].iup = 0;   // advance_init!: iup = 1  (mixed_population.jl:101)
+    CK(cudaMemsetAsync(ctx->d_sc->substeps, 0, (PTL_NSPECIES + 1) * sizeof(unsigned long long), ctx->stream));   // substeps[], births
+    for (int pi : M.pops) { ctx->pops[pi].iup = 0; ctx->pops[pi].rows_last = 0; }   // advance_init!: iup = 1  (mixed_population.jl:101)
     bool first = true;
     for (;;) {
         int32_t rc = sync_scalars(ctx); if (rc) return rc;     // read every popl.n (one host sync per pass)
@@ -968,10 +971,11 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
             long long rows = n - P.iup;
             if (rows > 0) {
                 const Table& T = ctx->tables[P.table];
-                rc = launch_advance(ctx, P.v.species, A, P.iup, n, first, has_cb, T.smem_bytes);
+                rc = launch_advance(ctx, P.v.species, A, P.iup, n, first, has_cb, T.smem_bytes, first && P.kappa_est >= 0 && P.kappa_est < 2.0);
                 if (rc) return rc;
                 total += rows;
                 ctx->stats.rows += rows;
+                P.rows_last += rows;
                 P.iup = n;
             }
         }
@@ -985,7 +989,13 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
         if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->stats.main_ms = ms;
         ctx->ev_pending = false;
     }
-    ctx->stats.substeps = (int64_t)ctx->h_sc->substeps;
+    ctx->stats.substeps = 0;
+    for (int sp = 0; sp < PTL_NSPECIES; sp++) ctx->stats.substeps += (int64_t)ctx->h_sc->substeps[sp];
+    // sub-steps per row of each population: picks the kernel of its next first pass (streaming below ~2, wavefront above)
+    for (int pi : M.pops) {
+        Pop& P = ctx->pops[pi];
+        if (P.rows_last > 0) P.kappa_est = (double)ctx->h_sc->substeps[P.v.species] / (double)P.rows_last;
+    }
     ctx->stats.births = (int64_t)ctx->h_sc->births;
     return ctx->h_sc->flags;
 }

@@ -94,7 +94,7 @@ struct AdvanceParams {
     int fast_force;                  // 1: the pusher is RK2 with one homogeneous E field and no B for every species (hot path)
     double fastE[3];                 // e * E  [N]; the species' charge sign / mass is applied in the kernel
     int* flags;                      // sticky PTL_ERR_* bits
-    unsigned long long* substeps;    // global sub-step counter
+    unsigned long long* substeps;    // sub-step counters, one per species
     unsigned long long* births;
 };
 
