@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libparticulator_b200.so")
 SOURCES = ["ptl_api.cu"]
-HEADERS = ["ptl_common.cuh", "ptl_physics.cuh", "ptl_advance.cuh", "ptl_advance_wf.cuh", "ptl_advance_aq.cuh", "ptl_store.cuh",
+HEADERS = ["ptl_common.cuh", "ptl_physics.cuh", "ptl_advance.cuh", "ptl_advance_wf.cuh", "ptl_advance_aq.cuh", "ptl_advance_bq.cuh", "ptl_store.cuh",
            os.path.join("..", "..", "include", "particulator_b200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

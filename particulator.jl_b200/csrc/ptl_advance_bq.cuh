@@ -1,0 +1,170 @@
+// ptl_advance_bq.cuh — K1, list-scheduled variant of the wavefront advance kernel (the default for leptons).
+//
+// k_advance_wf re-sorts every slot of the CTA every round (ballots, count matrix, two extra barriers: ~250 scheduler
+// instructions per warp and round = 30 % of all instructions in ncu, profiles/r1_v25_*).  Here the sort is incremental:
+// when a lane finishes a work unit it appends its slot to the shared-memory list of the slot's NEXT class (one
+// atomicAdd per destination class and warp, `__match_any_sync`), so at the single barrier that ends a round the
+// per-class lists of the next round are already built.  A round is then: read six counters, pick this warp's chunks
+// (32 consecutive entries of one class; full chunks first, then the largest remainders; what is not picked is carried
+// over and only grows), execute, append, barrier.  The pool holds BQ_SLOTS = 2 x threads slots and every warp
+// executes up to two chunks per round, which halves the barriers per unit and keeps the chunks full.
+// Work units, arithmetic, draw order and Philox streams are those of k_advance_wf (shared wf_execute_unit).
+#pragma once
+#include "ptl_advance_wf.cuh"
+
+namespace ptl {
+
+constexpr int BQ_THREADS = 256;
+constexpr int BQ_WARPS = BQ_THREADS / 32;
+constexpr int BQ_CPW = 2;                          // chunks per warp and round
+constexpr int BQ_SLOTS = BQ_THREADS * BQ_CPW;
+constexpr int BQ_NCLASS = WS_IDLE;                 // 6 lists
+constexpr int BQ_CHUNKS = BQ_WARPS * BQ_CPW;       // chunks executed per round
+
+constexpr size_t BQ_POOL_BYTES =
+    ((sizeof(double) * WD_NCOL * BQ_SLOTS + 16 * BQ_SLOTS + 4 * 5 * BQ_SLOTS + 2 * 2 * BQ_NCLASS * BQ_SLOTS + 4 * 3 * 8) + 15) / 16 * 16;
+
+template <int SP, int TK, bool FIRST, bool CB>
+__global__ void __launch_bounds__(BQ_THREADS, 2) k_advance_bq(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                              unsigned long long* row_counter, const long long* __restrict__ rows,
+                                                              const unsigned long long* __restrict__ nrows) {
+    if (rows != nullptr) { i0 = 0; i1 = (long long)*nrows; }     // index-list mode (rows deferred by the streaming kernel)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TableView& T = P.tab[SP];
+    const PopView& Q = P.pop[SP];
+    WfPool S;
+    S.np = BQ_SLOTS;
+    unsigned char* ptr = smem_raw;
+    S.d = reinterpret_cast<double*>(ptr); ptr += sizeof(double) * WD_NCOL * BQ_SLOTS;
+    S.uid = reinterpret_cast<unsigned long long*>(ptr); ptr += 8 * BQ_SLOTS;
+    S.row = reinterpret_cast<long long*>(ptr); ptr += 8 * BQ_SLOTS;
+    S.idx = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
+    S.cblock = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
+    S.c2 = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
+    S.c3 = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
+    S.state = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
+    S.cnt = nullptr;
+    S.order = nullptr;
+    unsigned short* lists = reinterpret_cast<unsigned short*>(ptr); ptr += 2 * 2 * BQ_NCLASS * BQ_SLOTS;   // [2][class][slot]
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(ptr);                                               // [3][8]
+    double* tsm = reinterpret_cast<double*>(smem_raw + BQ_POOL_BYTES);
+
+    const bool fastsel = (TK == 0) && T.order == 3 && T.nprocs <= 16;
+    const int nrate = (TK == 0) ? (fastsel ? WF_CUM_STRIDE * (T.k + 1) : T.order * T.nprocs * (T.k + 1)) : 0;
+    const int nrb = (TK == 0) ? T.order * (T.k + 1) : 0;
+    {
+        const int nproc_dbl = (T.nprocs * (int)sizeof(ptl_process_desc)) / 8;
+        const double* pd = reinterpret_cast<const double*>(T.procs);
+        if (fastsel) {
+            for (int q = threadIdx.x; q < nrate; q += blockDim.x) {
+                int i = q / WF_CUM_STRIDE, rr = q - i * WF_CUM_STRIDE;
+                int j = rr & 15, m = rr >> 4;
+                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
+            }
+        } else {
+            for (int q = threadIdx.x; q < nrate; q += blockDim.x) tsm[q] = T.cum[q];
+        }
+        for (int q = threadIdx.x; q < nrb; q += blockDim.x) tsm[nrate + q] = T.ratebound[q];
+        for (int q = threadIdx.x; q < nproc_dbl; q += blockDim.x) tsm[nrate + nrb + q] = pd[q];
+    }
+    const double* tcum = (TK == 0) ? tsm : T.cum;
+    SmemTable TS;
+    TS.rate = T.rate;
+    TS.ratebound = tsm + nrate;
+    TS.procs = reinterpret_cast<const ptl_process_desc*>(tsm + nrate + nrb);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    // round 0: every slot is an empty LOAD item
+    for (int q = tid; q < BQ_SLOTS; q += blockDim.x) { lists[q] = (unsigned short)q; S.state[q] = WS_LOAD; }
+    if (tid < 24) cnt[tid] = (tid == WS_LOAD) ? BQ_SLOTS : 0;
+    const RngCtx rc = {P.step, P.seed_lo, P.seed_hi};
+    const double cut = Q.energy_cut;
+    unsigned long long nsub = 0;
+    __syncthreads();
+
+    for (unsigned round = 0;; round++) {
+        const unsigned cb3 = round % 3;
+        const unsigned int* ccur = cnt + 8 * cb3;
+        unsigned int* cnxt = cnt + 8 * ((cb3 + 1) % 3);
+        unsigned int* cold = cnt + 8 * ((cb3 + 2) % 3);          // read in the previous round: safe to clear now
+        const unsigned short* lcur = lists + (round & 1) * (BQ_NCLASS * BQ_SLOTS);
+        unsigned short* lnxt = lists + ((round & 1) ^ 1) * (BQ_NCLASS * BQ_SLOTS);
+        if (tid < 8) cold[tid] = 0;
+
+        // ---- chunk plan, computed once per warp with lane c holding class c ----
+        // full chunks in class order, then the largest remainders (ties -> lower class) while chunks are left
+        const int n_c = lane < BQ_NCLASS ? (int)ccur[lane] : 0;
+        const int f_c = n_c >> 5, r_c = n_c & 31;
+        int incl = f_c;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const int start_c = incl - f_c;                          // first plan index of class c's full chunks
+        const int nfull = __shfl_sync(0xffffffffu, incl, BQ_NCLASS - 1);
+        int tot = n_c;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+        if (__shfl_sync(0xffffffffu, tot, 0) == 0) break;        // block-uniform: every slot retired
+        int rk_c = 0;
+#pragma unroll
+        for (int d = 0; d < BQ_NCLASS; d++) {
+            const int rd = __shfl_sync(0xffffffffu, r_c, d);
+            rk_c += (rd > r_c) || (rd == r_c && d < lane);
+        }
+        const int npartial = BQ_CHUNKS - nfull;                  // nfull <= BQ_CHUNKS because the pool has BQ_CHUNKS*32 slots
+        const bool part_c = lane < BQ_NCLASS && r_c > 0 && rk_c < npartial;
+        const int done_c = f_c * 32 + (part_c ? r_c : 0);        // entries of class c executed this round
+
+        // carry-over: what this round does not execute moves to the next round's lists (warp c handles class c)
+        if (wid < BQ_NCLASS) {
+            const int nn = __shfl_sync(0xffffffffu, n_c, wid), done = __shfl_sync(0xffffffffu, done_c, wid);
+            const int left = nn - done;
+            if (left > 0) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&cnxt[wid], (unsigned)left);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int q = lane; q < left; q += 32) lnxt[wid * BQ_SLOTS + base + q] = lcur[wid * BQ_SLOTS + done + q];
+            }
+        }
+
+        // ---- execute this warp's chunks ----
+#pragma unroll 1
+        for (int cw = 0; cw < BQ_CPW; cw++) {
+            const int chunk = wid + cw * BQ_WARPS;               // index in the plan order
+            const unsigned mfull = __ballot_sync(0xffffffffu, lane < BQ_NCLASS && chunk >= start_c && chunk < start_c + f_c);
+            const unsigned mpart = __ballot_sync(0xffffffffu, part_c && rk_c == chunk - nfull);
+            const unsigned msel = mfull ? mfull : mpart;
+            int it = -1;
+            if (msel) {
+                const int my_c = __ffs(msel) - 1;
+                const int k0 = mfull ? (chunk - __shfl_sync(0xffffffffu, start_c, my_c)) : __shfl_sync(0xffffffffu, f_c, my_c);
+                const int nn = __shfl_sync(0xffffffffu, n_c, my_c);
+                const int pos = k0 * 32 + lane;
+                if (pos < nn) it = (int)lcur[my_c * BQ_SLOTS + pos];
+            }
+            const bool has = it >= 0;
+            const unsigned amask = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                const uint32_t sw = S.state[it];
+                wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, amask, lane, ltmask, row_counter, i0, i1, nsub, rows);
+                __syncwarp(amask);
+                const int nc = (int)(S.state[it] & 0xffu);       // next class; IDLE slots are retired
+                const unsigned grp = __match_any_sync(amask, nc);
+                if (nc < BQ_NCLASS) {
+                    const int leader = __ffs(grp) - 1;
+                    unsigned pos = 0;
+                    if (lane == leader) pos = atomicAdd(&cnxt[nc], (unsigned)__popc(grp));
+                    pos = __shfl_sync(grp, pos, leader) + __popc(grp & ltmask);
+                    lnxt[nc * BQ_SLOTS + pos] = (unsigned short)it;
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+    for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
+    if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
+}
+
+}  // namespace ptl

@@ -11,7 +11,10 @@
 
 #include "ptl_advance.cuh"
 #include "ptl_advance_wf.cuh"
-#include "ptl_advance_aq.cuh"
+#ifdef PTL_WITH_AQ
+#include "ptl_advance_aq.cuh"   // queue-driven experiment (autonomous warps); not faster than the list-scheduled kernel
+#endif
+#include "ptl_advance_bq.cuh"
 #include "ptl_store.cuh"
 
 using namespace ptl;
@@ -96,7 +99,7 @@ struct ptl_context {
     size_t tmp_bytes = 0;
     long long* d_slow_rows = nullptr;  // rows the streaming photon kernel deferred to the general kernel
     size_t slow_cap = 0;
-    int kernel_mode = 0;               // PTL_KERNEL=aq selects the queue-driven lepton kernel, =wf the barrier-synchronous one
+    int kernel_mode = 0;               // PTL_KERNEL: wf / aq = alternative lepton kernels, nostream = no streaming fast path (A/B measurements)
     long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -246,6 +249,7 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     return 0;
 }
 
+#ifdef PTL_WITH_AQ
 // queue-driven variant: autonomous warps, per-class ring buffers in shared memory
 template <int SP, int TK, bool FIRST, bool CB>
 int32_t launch_advance_aq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1) {
@@ -277,11 +281,52 @@ int32_t launch_advance_aq_k(ptl_context* ctx, const AdvanceParams& A, long long 
     return 0;
 }
 
+#endif
+
+// list-scheduled variant (incremental per-class lists, one barrier per round, two chunks per warp)
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_bq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, const long long* rows) {
+    auto kern = k_advance_bq<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    size_t smem = BQ_POOL_BYTES + tsm + 32;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        configured = true;
+    }
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, BQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long nrow = i1 - i0;
+    long long want = (nrow + BQ_SLOTS - 1) / BQ_SLOTS;
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, BQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
 template <int SP, bool FIRST, bool CB>
 int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows = nullptr) {
+    // default: list-scheduled kernel (k_advance_bq).  PTL_KERNEL=wf selects the re-sorting kernel, PTL_KERNEL=aq the
+    // queue-driven one (only when compiled with -DPTL_WITH_AQ) — kept for A/B measurements.
+#ifdef PTL_WITH_AQ
     if (ctx->kernel_mode == 1 && rows == nullptr) {
         if (A.tab[SP].kind == 0) return launch_advance_aq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1);
         return launch_advance_aq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1);
+    }
+#endif
+    if (ctx->kernel_mode != 4) {
+        if (A.tab[SP].kind == 0) return launch_advance_bq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, rows);
+        return launch_advance_bq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, rows);
     }
     if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
     return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
@@ -367,7 +412,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     ptl_context* ctx = new ptl_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : (!strcmp(km, "nostream") ? 2 : 0);
+    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : (!strcmp(km, "nostream") ? 2 : (!strcmp(km, "wf") ? 4 : 0));
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
