@@ -330,44 +330,88 @@ def main():
         d = el.download()
         n_e2e = len(d["w"])
         host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()}
-        out = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
         del d
         import ctypes as C
         b = ctx.backend
 
-        def ptr(tn, ty):
-            return C.cast(tn.data_ptr(), C.POINTER(ty))
+        def ptr(tn, ty, off=0):
+            return C.cast(tn.data_ptr() + off * tn.element_size() * (tn.shape[1] if tn.dim() > 1 else 1), C.POINTER(ty))
 
+        # The population is cut into independent shards (particles never interact) that two host threads push through
+        # their own library contexts: while one context advances a shard, the other one's H2D / D2H copies run on the
+        # copy engines.  Every byte still crosses PCIe inside the timed region.
+        nshards, nworkers = 4, 2
+        bounds = [n_e2e * k // nshards for k in range(nshards + 1)]
+        shard_cap = int(1.7 * (bounds[1] - bounds[0])) + 8192
+        workers = []
+        for wk in range(nworkers):
+            wctx = P.Context(device=local_rank)                       # own non-blocking stream
+            wmp, wel, wph, wpo = make_world(P, wctx, tables, shard_cap, max(shard_cap // 3, 1 << 20), max(shard_cap // 16, 1 << 18))
+            wctx.set_rng(rank * 16 + wk + 1, 0)
+            workers.append((wctx, wmp, wel, psh.desc(wctx)))
+        got_rows = [0] * nshards
+        out_cap = [int(1.3 * (bounds[k + 1] - bounds[k])) + 4096 for k in range(nshards)]
+        out = [{k: torch.empty((out_cap[sh],) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in host.items()} for sh in range(nshards)]
+        t_loc = float(host["t"][0]) + DT
+        errors = []
+
+        def work(wk):
+            wctx, wmp, wel, pd = workers[wk]
+            try:
+                for sh in range(wk, nshards, nworkers):
+                    lo, m = bounds[sh], bounds[sh + 1] - bounds[sh]
+                    rc = b.population_upload(wctx.h, wel.id, m, ptr(host["x"], C.c_double, lo), ptr(host["p"], C.c_double, lo),
+                                             ptr(host["w"], C.c_double, lo), ptr(host["t"], C.c_double, lo), ptr(host["s"], C.c_double, lo),
+                                             ptr(host["r"], C.c_double, lo), ptr(host["active"], C.c_uint8, lo), ptr(host["uid"], C.c_uint64, lo))
+                    assert rc == 0, rc
+                    rc = b.advance(wctx.h, wmp.id, C.byref(pd), t_loc, None)
+                    assert rc >= 0, rc
+                    for q in wmp:
+                        b.droplow(wctx.h, q.id, 0.0)
+                    o = out[sh]
+                    got_rows[sh] = int(b.population_download(wctx.h, wel.id, out_cap[sh], ptr(o["x"], C.c_double), ptr(o["p"], C.c_double),
+                                                             ptr(o["w"], C.c_double), ptr(o["t"], C.c_double), ptr(o["s"], C.c_double),
+                                                             ptr(o["r"], C.c_double), ptr(o["active"], C.c_uint8), ptr(o["uid"], C.c_uint64)))
+                    assert got_rows[sh] > 0
+                    # photons / positrons born in this shard stay on the device (they are results of later steps' inputs)
+                    b.population_clear(wctx.h, list(wmp)[1].id)
+                    b.population_clear(wctx.h, list(wmp)[2].id)
+            except Exception as exc:  # pragma: no cover
+                errors.append(repr(exc))
+
+        def one_e2e_step():
+            ths = [threading.Thread(target=work, args=(wk,)) for wk in range(nworkers)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+
+        one_e2e_step()                                                # untimed warm-up (lazy module loading, allocations)
         barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
+        t0 = time.perf_counter()
         e2e_psteps = 0
-        pd = psh.desc(ctx)
+        d2h_rows = 0
         for k in range(args.e2e_steps):
-            rc = b.population_upload(ctx.h, el.id, n_e2e, ptr(host["x"], C.c_double), ptr(host["p"], C.c_double), ptr(host["w"], C.c_double),
-                                     ptr(host["t"], C.c_double), ptr(host["s"], C.c_double), ptr(host["r"], C.c_double),
-                                     ptr(host["active"], C.c_uint8), ptr(host["uid"], C.c_uint64))
-            assert rc == 0, rc
-            t_loc = float(host["t"][0]) + DT
-            rc = b.advance(ctx.h, mp.id, C.byref(pd), t_loc, None)
-            assert rc >= 0, rc
-            for q in mp:
-                b.droplow(ctx.h, q.id, 0.0)
-            got = b.population_download(ctx.h, el.id, n_e2e, ptr(out["x"], C.c_double), ptr(out["p"], C.c_double), ptr(out["w"], C.c_double),
-                                        ptr(out["t"], C.c_double), ptr(out["s"], C.c_double), ptr(out["r"], C.c_double),
-                                        ptr(out["active"], C.c_uint8), ptr(out["uid"], C.c_uint64))
-            assert got > 0
+            one_e2e_step()
             e2e_psteps += n_e2e
-        f1.record()
+            d2h_rows += sum(got_rows)
+        torch.cuda.synchronize()
+        e2e_elapsed = (time.perf_counter() - t0) * 1e3
         barrier()
-        e2e_ms = torch.tensor([f0.elapsed_time(f1)], device="cuda", dtype=torch.float64)
+        assert not errors, errors
+        e2e_ms = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
         e2e_ps = torch.tensor([float(e2e_psteps)], device="cuda", dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(e2e_ps, op=dist.ReduceOp.SUM)
         e2e = {"value": float(e2e_ps.item()) / (float(e2e_ms.item()) * 1e-3), "unit": "particle-steps/s",
-               "h2d_bytes_per_step": 89 * n_e2e, "d2h_bytes_per_step": 89 * min(n_e2e, int(got)), "steps": args.e2e_steps,
-               "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download"}
+               "h2d_bytes_per_step": 89 * n_e2e, "d2h_bytes_per_step": 89 * d2h_rows // max(args.e2e_steps, 1), "steps": args.e2e_steps,
+               "ms_per_step": float(e2e_ms.item()) / max(args.e2e_steps, 1),
+               "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download, "
+                       f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other)",
+               "timer": "host wall clock between device-wide synchronizes (work spans several streams)"}
+        for wctx, *_ in workers:
+            wctx.close()
 
     # ---- CPU baseline on the host cores of this box (rank 0, N = 1 only) ----
     cpu = None
