@@ -397,3 +397,95 @@ def test_statistical_agreement_over_seeds(gctx, octx, air_tables):
     for k in range(3):
         sigma = np.sqrt(g[:, k].var(ddof=1) / 6 + o[:, k].var(ddof=1) / 6)
         assert abs(g[:, k].mean() - o[:, k].mean()) <= 3 * sigma + 1e-12, (k, g[:, k].mean(), o[:, k].mean(), sigma)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the general forcing / pusher stack (pusher.jl:8-76, field.jl:4-70, continuum.jl) and the remaining processes
+# ---------------------------------------------------------------------------------------------------
+def _pushers():
+    nel = co.nair * 14.4
+    cl = P.ContinuumLoss(nel, 85.7 * co.eV, 1e3 * co.eV)
+    ccl = P.ChebContinuumLoss.from_loss(cl, 3e8 * co.eV, 4)
+    E = [0.0, 0.0, -5e5]
+    return {
+        "double_layer+B": P.RK2Pusher(P.ElectromagneticField(P.DoubleLayerField(-0.5, 0.5, E), P.HomogeneousField([0.0, 2e-4, 1e-4]))),
+        "step": P.RK2Pusher(P.ElectromagneticField(P.StepField(0.0, [1e5, 0.0, -5e5], [0.0, -2e5, 5e5]), None)),
+        "confined": P.RK2Pusher(P.ElectromagneticField(P.ConfinedDoubleLayerField(2.0, 3.0, 1.5, -8e5), P.HomogeneousField([0.0, 0.0, 5e-5]))),
+        "em+continuum": P.RK2Pusher(P.CombinedForcing(P.ElectromagneticField(P.HomogeneousField(E), P.HomogeneousField([0, 0, 0])), cl)),
+        "em+cheb_continuum": P.RK2Pusher(P.CombinedForcing(P.ElectromagneticField(P.HomogeneousField(E), None), ccl)),
+        "restricted_forcing": P.RK2Pusher(P.CombinedForcing(P.RestrictedForcing(P.POSITRON, P.ElectromagneticField(P.HomogeneousField(E), None)),
+                                                            P.RestrictedForcing(P.ELECTRON, cl))),
+        "restricted_pusher": P.RestrictedPusher(P.ELECTRON, P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField(E), None))),
+        "null_pusher": P.NullPusher(),
+    }
+
+
+@pytest.mark.parametrize("name", ["double_layer+B", "step", "confined", "em+continuum", "em+cheb_continuum", "restricted_forcing",
+                                  "restricted_pusher", "null_pusher"])
+def test_forcing_and_pusher_stack_replay(gctx, octx, air_tables, name):
+    worlds = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(17, 0)
+        worlds.append(make_world(ctx, air_tables, 1500, 600, 700, cap=30000, seed=21, emin=3e3, emax=2e7))
+    psh = _pushers()[name]
+    for mp, *_ in worlds:
+        P.advance(mp, psh, DT)
+    sg, so = P.last_advance_stats(worlds[0][0]), P.last_advance_stats(worlds[1][0])
+    assert abs(sg["substeps"] - so["substeps"]) <= 2e-3 * so["substeps"] + 50
+    for k, label in ((1, "electron"), (2, "photon"), (3, "positron")):
+        _compare_populations(worlds[0][k], worlds[1][k], f"{name}/{label}")
+    assert gctx.error_flags(clear=True) == octx.error_flags(clear=True)
+
+
+def test_moller_and_klein_nishina_tables_replay(gctx, octx):
+    """Processes that the air tables of scripts/beam.jl do not use: Moller (moller.jl) with continuum losses below the
+    cut, and the closed-form Klein-Nishina cross-section (compton.jl:34-47)."""
+    from particulator_b200 import tables
+    n2 = co.nair
+    et = tables.collision_table_from_processes([(2 * n2, P.RelativisticCoulomb(7)), (14 * n2, P.Moller(1, 1e3 * co.eV))], P.ELECTRON,
+                                               co.elementary_charge * 5e5 * DT, safety=1.15)
+    gt = tables.collision_table_from_processes([(2 * n2, P.KleinNishinaCompton(7)), (2 * n2, P.PhotoElectric(7))], P.PHOTON, 0)
+    for tab, species, lo in ((et, P.ELECTRON, 3e3), (gt, P.PHOTON, 2e3)):
+        gctx.set_rng(5, 2)
+        octx.set_rng(5, 2)
+        for j, proc in enumerate(tab.proc):
+            p3 = _momenta(species, 10000, lo, 5e7, 300 + j)
+            g = gctx.collide_test(species, tab, j, p3, uid0=77)
+            o = octx.collide_test(species, tab, j, p3, uid0=77)
+            same = (g[:, 3] == o[:, 3]) & (g[:, 0] == o[:, 0])
+            assert (~same).sum() <= 2, proc.name
+            scale = np.linalg.norm(p3, axis=1)[same, None]
+            for c0 in (4, 8):
+                assert (np.abs(g[same, c0:c0 + 3] - o[same, c0:c0 + 3]) / scale).max() <= EVENT_RTOL, proc.name
+    # a full step with the Moller table + continuum friction
+    cl = P.ContinuumLoss(co.nair * 14.4, 85.7 * co.eV, 1e3 * co.eV)
+    psh = P.RK2Pusher(P.CombinedForcing(P.ElectromagneticField(P.HomogeneousField([0, 0, -5e5]), None), cl))
+    pops = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(8, 0)
+        rng = np.random.default_rng(31)
+        p3 = _momenta(P.ELECTRON, 3000, 5e3, 2e7, 9)
+        st = dict(x=np.zeros((3000, 3)), p=p3, s=-np.log(1 - rng.random(3000)), uid=np.arange(1, 3001, dtype=np.uint64))
+        el = P.Population(ctx, P.ELECTRON, 30000, st, et, 1e3 * co.eV)
+        mp = P.MultiPopulation(("electron", el))
+        P.advance(mp, psh, DT)
+        pops.append(el)
+    _compare_populations(pops[0], pops[1], "moller step")
+
+
+def test_empty_and_inactive_populations(gctx, air_tables):
+    mp, el, ph, po = make_world(gctx, air_tables, 0, 0, 0, cap=1024)
+    assert P.advance(mp, default_pusher(), DT) == 0
+    assert P.last_advance_stats(mp)["substeps"] == 0
+    assert [len(q) for q in mp] == [0, 0, 0]
+    assert P.droplow(el) == 0 and P.repack(el) == 0
+    assert P.nactives(el) == 0
+    # a population whose rows are all inactive is skipped (l.active || continue) and compacts to nothing
+    st = _random_pop(np.random.default_rng(0), 500, 1.0)
+    el2 = P.Population(gctx, P.ELECTRON, 1000, st, air_tables["electron"], 1e3 * co.eV)
+    mp2 = P.MultiPopulation(("electron", el2))
+    P.advance(mp2, default_pusher(), DT)
+    assert P.last_advance_stats(mp2)["substeps"] == 0
+    after = el2.download()
+    assert np.array_equal(after["t"], st["t"]) and np.array_equal(after["p"], st["p"])
+    assert P.droplow(el2) == 0
