@@ -14,9 +14,18 @@
 
 namespace ptl {
 
-constexpr int BQ_THREADS = 256;
+#ifndef BQ_THREADS_MACRO
+#define BQ_THREADS_MACRO 256
+#endif
+constexpr int BQ_THREADS = BQ_THREADS_MACRO;
 constexpr int BQ_WARPS = BQ_THREADS / 32;
-constexpr int BQ_CPW = 2;                          // chunks per warp and round
+#ifndef BQ_CPW_MACRO
+#define BQ_CPW_MACRO 2
+#endif
+#ifndef BQ_MIN_BLOCKS
+#define BQ_MIN_BLOCKS 2
+#endif
+constexpr int BQ_CPW = BQ_CPW_MACRO;               // chunks per warp and round
 constexpr int BQ_SLOTS = BQ_THREADS * BQ_CPW;
 constexpr int BQ_NCLASS = WS_IDLE;                 // 6 lists
 constexpr int BQ_CHUNKS = BQ_WARPS * BQ_CPW;       // chunks executed per round
@@ -25,7 +34,7 @@ constexpr size_t BQ_POOL_BYTES =
     ((sizeof(double) * WD_NCOL * BQ_SLOTS + 16 * BQ_SLOTS + 4 * 5 * BQ_SLOTS + 2 * 2 * BQ_NCLASS * BQ_SLOTS + 4 * 3 * 8) + 15) / 16 * 16;
 
 template <int SP, int TK, bool FIRST, bool CB>
-__global__ void __launch_bounds__(BQ_THREADS, 2) k_advance_bq(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+__global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                               unsigned long long* row_counter, const long long* __restrict__ rows,
                                                               const unsigned long long* __restrict__ nrows) {
     if (rows != nullptr) { i0 = 0; i1 = (long long)*nrows; }     // index-list mode (rows deferred by the streaming kernel)
@@ -116,14 +125,14 @@ __global__ void __launch_bounds__(BQ_THREADS, 2) k_advance_bq(const __grid_const
         const int done_c = f_c * 32 + (part_c ? r_c : 0);        // entries of class c executed this round
 
         // carry-over: what this round does not execute moves to the next round's lists (warp c handles class c)
-        if (wid < BQ_NCLASS) {
-            const int nn = __shfl_sync(0xffffffffu, n_c, wid), done = __shfl_sync(0xffffffffu, done_c, wid);
+        for (int c = wid; c < BQ_NCLASS; c += BQ_WARPS) {
+            const int nn = __shfl_sync(0xffffffffu, n_c, c), done = __shfl_sync(0xffffffffu, done_c, c);
             const int left = nn - done;
             if (left > 0) {
                 unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&cnxt[wid], (unsigned)left);
+                if (lane == 0) base = atomicAdd(&cnxt[c], (unsigned)left);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                for (int q = lane; q < left; q += 32) lnxt[wid * BQ_SLOTS + base + q] = lcur[wid * BQ_SLOTS + done + q];
+                for (int q = lane; q < left; q += 32) lnxt[c * BQ_SLOTS + base + q] = lcur[c * BQ_SLOTS + done + q];
             }
         }
 
