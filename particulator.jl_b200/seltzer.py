@@ -76,7 +76,7 @@ def findcumvalues(x, p, pcum, xmin, xmax, rtol=1e-6):
         xsol = 0.5 * (lo + hi)
         dx = math.inf
         it = 0
-        while abs(dx / xsol) > rtol:
+        while xsol != 0.0 and abs(dx / xsol) > rtol:     # Julia: abs(Inf/0)=Inf loops, abs(x/0)=NaN/Inf at xsol == 0 stops only via NaN; the k/T = 1 end point is exact
             f = (float(ci(xsol)) - cum0) / (cum1 - cum0)
             df = float(ci.density(xsol)) / (cum1 - cum0)
             dx = (f - pc) / df
