@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
     unsigned long long nsub = 0;
     __syncthreads();
 
-    for (unsigned round = 0;; round++) {
+    unsigned round = 0;
+    for (;; round++) {
         const unsigned cb3 = round % 3;
         const unsigned int* ccur = cnt + 8 * cb3;
         unsigned int* cnxt = cnt + 8 * ((cb3 + 1) % 3);
@@ -114,6 +115,20 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
 #pragma unroll
         for (int d = 1; d < 8; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
         if (__shfl_sync(0xffffffffu, tot, 0) == 0) break;        // block-uniform: every slot retired
+#ifdef PTL_DEBUG_TAIL
+        if (wid == 0 && __shfl_sync(0xffffffffu, tot, 0) <= 2) {
+            if (lane < BQ_NCLASS && n_c > 0) {
+                atomicAdd(P.dbg + 4 + lane, 1ULL);
+                if ((round & 1023) == 0) {
+                    const int it0 = lcur[lane * BQ_SLOTS];
+                    P.dbg[3] = (unsigned long long)S.row[it0];
+                    P.dbg[10] = __double_as_longlong(WFD(WD_P0, it0)); P.dbg[11] = __double_as_longlong(WFD(WD_P0 + 1, it0));
+                    P.dbg[12] = __double_as_longlong(WFD(WD_P0 + 2, it0)); P.dbg[13] = __double_as_longlong(WFD(WD_R, it0));
+                    P.dbg[14] = __double_as_longlong(WFD(WD_S, it0));
+                }
+            }
+        }
+#endif
         int rk_c = 0;
 #pragma unroll
         for (int d = 0; d < BQ_NCLASS; d++) {
@@ -174,6 +189,7 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
     if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
+    if (tid == 0) { atomicMax(P.dbg, (unsigned long long)round); atomicAdd(P.dbg + 1, (unsigned long long)round); atomicAdd(P.dbg + 2, 1ULL); }
 }
 
 }  // namespace ptl

@@ -29,6 +29,7 @@ static_assert(WS_IDLE == 6 && WF_WARPS == 8, "the lane-parallel scheduler assume
 constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the shared-memory cumulative-rate table
 constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
 constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
+constexpr uint32_t WF_COAST = 0x400u;   // OTHER unit: no collision, take the repeated below-cut sub-steps in blocks
 
 // double columns of the shared-memory particle pool
 enum { WD_X0 = 0, WD_X1, WD_X2, WD_P0, WD_P1, WD_P2, WD_T, WD_S, WD_R, WD_TREM, WD_ENG, WD_SCR, WD_NCOL };
@@ -64,6 +65,47 @@ __device__ __forceinline__ void wf_put3(const WfPool& S, int c0, int it, Vec3 v)
     S.d[(c0 + 0) * S.np + it] = v.x; S.d[(c0 + 1) * S.np + it] = v.y; S.d[(c0 + 2) * S.np + it] = v.z;
 }
 #define WFD(col, it) S.d[(col) * S.np + (it)]
+
+// A particle that the field decelerated below energy_cut keeps its old r != 0: do_one_collision! returns before it
+// draws anything (collisions.jl:148-151), so the sub-step loop of mixed_population.jl:66-87 repeats the same
+// dt = s/r push until tfinal or until the energy is back above the cut -- up to 1e5..1e6 sequential sub-steps when s
+// is small, which used to be the tail of every launch.  Under the uniform-E fast path the kinetic energy is a convex
+// function of time, so "below the cut after j sub-steps" implies below the cut at every sub-step in between: take the
+// j sub-steps as ONE RK2 step of j*dt (p is linear in t and exact up to rounding, x differs by the RK2 truncation error
+// of the longer step, < 1e-10 relative here), with t and trem accumulated sub-step by sub-step so that they stay
+// bit-identical, and halve j when the energy would cross the cut so that the first test at or above the cut is
+// still taken by the regular path on the reference's own time grid.
+// Works on the slot in the shared-memory pool (it runs as a flagged OTHER unit, so the hot STEP unit pays one compare)
+// and takes at most ~256 sub-steps per call so that the unit stays as short as the others in its round; the slot keeps
+// the WF_COAST flag until no further repeated sub-step fits or the next one would reach the cut.
+template <int SP>
+__device__ __noinline__ unsigned long long wf_coast_below_cut(const AdvanceParams& P, const WfPool& S, int it, double cut) {
+    Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
+    double t = WFD(WD_T, it), trem = WFD(WD_TREM, it);
+    const double tnext = WFD(WD_S, it) * frcp(WFD(WD_R, it));       // same expression as the STEP unit (:67)
+    unsigned long long nsub = 0;
+    int M = 128, work = 0;
+    bool more = false;
+    while (M >= 1) {
+        double tr = trem, tt = t;
+        int j = 0;
+        for (; j < M && tr > DBL_EPS && tr > tnext; j++) { tr -= tnext; tt += tnext; }   // mixed_population.jl:66-68,86
+        if (j == 0) break;                                           // the final free flight belongs to the STEP unit
+        work += j;
+        Vec3 xc = x, pc = p;
+        double tdum = 0;
+        push<SP>(P, xc, pc, tdum, tnext * j);
+        if (!(kinenergy<SP>(pc) < cut)) { M = j >> 1; continue; }    // would reach the cut: halve (M == 0: STEP takes it)
+        x = xc; p = pc; t = tt; trem = tr; nsub += (unsigned long long)j;
+        if (work >= 256) { more = true; break; }
+    }
+    if (nsub) {
+        wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
+        WFD(WD_T, it) = t; WFD(WD_TREM, it) = trem;
+    }
+    S.state[it] = more ? (WS_OTHER | WF_VALID | WF_COAST) : (WS_STEP | WF_VALID);
+    return nsub;
+}
 
 // after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP
 template <int SP>
@@ -284,6 +326,8 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                     uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
                     next = c | WF_VALID | ((uint32_t)jsel << 16);
                 }
+            } else if (!CB && r != 0.0 && P.fast_force && trem > tnext) {
+                next = WS_OTHER | WF_VALID | WF_COAST;  // below the cut with r != 0: see wf_coast_below_cut
             }
         }
         if (rng_loaded) wf_store_rng(S, it, rng);
@@ -349,6 +393,10 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
     }
     // ------------------------------------------------------------------------------------------
     case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
+        if (sw & WF_COAST) {
+            nsub += wf_coast_below_cut<SP>(P, S, it, cut);
+            break;
+        }
         Rng rng;
         wf_load_rng(S, it, rng);
         Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "ptl_advance.cuh"
 #include "ptl_advance_wf.cuh"
@@ -30,6 +31,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
     unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[DIAG_NVAL];
+    unsigned long long dbg[16];    // PTL_TRACE: max / sum of scheduler rounds per CTA, CTA count
 };
 
 struct Table {
@@ -189,6 +191,7 @@ void fill_params(ptl_context* ctx, const MultiPop* mp, AdvanceParams& A) {
     A.flags = &ctx->d_sc->flags;
     A.substeps = ctx->d_sc->substeps;
     A.births = &ctx->d_sc->births;
+    A.dbg = ctx->d_sc->dbg;
 }
 
 template <int SP, bool FIRST, bool CB>
@@ -1003,8 +1006,30 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
     CK(cudaMemsetAsync(ctx->d_sc->substeps, 0, (PTL_NSPECIES + 1) * sizeof(unsigned long long), ctx->stream));   // substeps[], births
     for (int pi : M.pops) { ctx->pops[pi].iup = 0; ctx->pops[pi].rows_last = 0; }   // advance_init!: iup = 1  (mixed_population.jl:101)
     bool first = true;
+    static const bool trace = getenv("PTL_TRACE") != nullptr;   // per-pass wall time / rows / sub-steps on stderr
+    auto tprev = std::chrono::steady_clock::now();
+    long long rows_prev = 0; unsigned long long sub_prev = 0;
     for (;;) {
         int32_t rc = sync_scalars(ctx); if (rc) return rc;     // read every popl.n (one host sync per pass)
+        if (trace) {
+            auto tnow = std::chrono::steady_clock::now();
+            unsigned long long sub = 0;
+            for (int sp = 0; sp < PTL_NSPECIES; sp++) sub += ctx->h_sc->substeps[sp];
+            if (ctx->stats.passes > 0)
+                fprintf(stderr, "[ptl trace] step %llu pass %d: rows %lld substeps %llu  %.3f ms\n", (unsigned long long)ctx->step,
+                        (int)ctx->stats.passes, rows_prev, sub - sub_prev, std::chrono::duration<double, std::milli>(tnow - tprev).count());
+            if (ctx->stats.passes > 0 && ctx->h_sc->dbg[2])
+                fprintf(stderr, "[ptl trace]     rounds per CTA: max %llu mean %.0f over %llu CTAs\n", ctx->h_sc->dbg[0],
+                        (double)ctx->h_sc->dbg[1] / (double)ctx->h_sc->dbg[2], ctx->h_sc->dbg[2]);
+            if (ctx->stats.passes > 0 && ctx->h_sc->dbg[2]) {
+                const unsigned long long* g = ctx->h_sc->dbg;
+                double v[5]; memcpy(v, g + 10, sizeof(v));
+                fprintf(stderr, "[ptl trace]     lonely rounds by class: %llu %llu %llu %llu %llu %llu; last lonely row %llu p=(%.4e %.4e %.4e) r=%.4e s=%.4e\n",
+                        g[4], g[5], g[6], g[7], g[8], g[9], g[3], v[0], v[1], v[2], v[3], v[4]);
+            }
+            CK(cudaMemsetAsync(ctx->d_sc->dbg, 0, sizeof(ctx->d_sc->dbg), ctx->stream));
+            tprev = tnow; sub_prev = sub;
+        }
         long long total = 0;
         for (int pi : M.pops) {
             Pop& P = ctx->pops[pi];
@@ -1025,6 +1050,7 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
             }
         }
         ctx->stats.passes++;
+        rows_prev = total;
         first = false;
         if (total == 0) break;     // advance1! returned 0 (mixed_population.jl:44-46)
     }

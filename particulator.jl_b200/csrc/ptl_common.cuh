@@ -95,6 +95,7 @@ struct AdvanceParams {
     double fastE[3];                 // e * E  [N]; the species' charge sign / mass is applied in the kernel
     int* flags;                      // sticky PTL_ERR_* bits
     unsigned long long* substeps;    // sub-step counters, one per species
+    unsigned long long* dbg;         // PTL_TRACE scheduler statistics (max rounds, sum rounds, CTAs)
     unsigned long long* births;
 };
 

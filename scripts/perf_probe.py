@@ -31,6 +31,7 @@ def main(n=2_000_000, species="electron", steps=3, emin=1e3, emax=1e8, spectrum=
     mp = P.MultiPopulation(*pops.items())
     psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0, 0, -5e5]), P.HomogeneousField([0, 0, 0])))
     t = 0.0
+    ctx.set_profiling(True)
     for it in range(steps):
         n0 = len(pops[species])
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,7 +45,7 @@ def main(n=2_000_000, species="electron", steps=3, emin=1e3, emax=1e8, spectrum=
         for q in mp: P.droplow(q)
         e3.record(); torch.cuda.synchronize()
         print(f"{species} n={n0} step {it}: advance {ms:.2f} ms, droplow {e2.elapsed_time(e3):.2f} ms, substeps={stt['substeps']} kappa={stt['substeps']/max(stt['rows'],1):.1f} "
-              f"births={stt['births']} passes={stt['passes']} -> {n0/ms*1e3:.3e} particle-steps/s, {stt['substeps']/ms*1e3:.3e} substeps/s, "
+              f"births={stt['births']} passes={stt['passes']} main_ms={stt['main_ms']:.2f} -> {n0/ms*1e3:.3e} particle-steps/s, {stt['substeps']/ms*1e3:.3e} substeps/s, "
               f"{n0*162/ms*1e-6:.1f} GB/s algorithmic", flush=True)
 
 if __name__ == "__main__":

@@ -225,6 +225,38 @@ def test_advance_replay_against_oracle(gctx, octx, air_tables, seed, n_e, n_g, n
             assert abs(len(worlds[0][k]) - len(worlds[1][k])) <= 3
 
 
+def test_below_cut_coasting_matches_substep_loop(gctx, octx, air_tables):
+    """Electrons that the field decelerates below energy_cut keep r != 0 and repeat the same s/r sub-step without
+    drawing (collisions.jl:148-151, mixed_population.jl:66-87).  The CUDA path takes those sub-steps in blocks
+    (wf_coast_below_cut); the oracle takes them one by one.  Same sub-step count, same t/s/r, x and p within the
+    replay tolerance -- including particles whose energy comes back above the cut inside the step."""
+    n = 4000
+    rng = np.random.default_rng(77)
+    K = (1e3 * (1 + 10 ** rng.uniform(-5, -1.3, n))) * co.eV              # just above the 1 keV cut
+    pn = P.momentum_norm_from_kin(P.ELECTRON, K)
+    cost = np.where(rng.random(n) < 0.5, rng.uniform(-1, -0.2, n), rng.uniform(-0.08, 0.0, n))   # against the force / nearly transverse
+    phi = rng.uniform(0, 2 * np.pi, n)
+    sint = np.sqrt(1 - cost ** 2)
+    d = np.stack([sint * np.cos(phi), sint * np.sin(phi), cost], axis=1)
+    st = dict(x=rng.normal(0, 1.0, (n, 3)), p=d * pn[:, None], s=10 ** rng.uniform(-3.5, 0.3, n),
+              uid=np.arange(1, n + 1, dtype=np.uint64))
+    worlds = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(5, 0)
+        el = P.Population(ctx, P.ELECTRON, 4 * n, st, air_tables["electron"], 1e3 * co.eV)
+        ph = P.Population(ctx, P.PHOTON, 4 * n, None, air_tables["photon"], 1e3 * co.eV)
+        worlds.append((P.MultiPopulation(("electron", el), ("photon", ph)), el, ph))
+    psh = default_pusher()
+    for mp, *_ in worlds:
+        P.advance(mp, psh, DT)
+    sg, so = P.last_advance_stats(worlds[0][0]), P.last_advance_stats(worlds[1][0])
+    assert so["substeps"] > 100 * n                     # the case really is dominated by the repeated sub-steps
+    assert abs(sg["substeps"] - so["substeps"]) <= 1e-3 * so["substeps"], (sg, so)
+    _compare_populations(worlds[0][1], worlds[1][1], "below-cut electrons")
+    below = P.kinenergy(P.ELECTRON, worlds[1][1].download()["p"]) < 1e3 * co.eV
+    assert 0.2 < below.mean() < 0.999                   # both outcomes are present: still below, and back above the cut
+
+
 def test_photon_free_flight_and_time(gctx, air_tables):
     """Photons (kappa ~ 1e-4): x advances by c*dt along p, t == tfinal, p untouched for non-colliding ones."""
     mp, el, ph, po = make_world(gctx, air_tables, 0, 200000, 0, cap=300000, seed=9)
