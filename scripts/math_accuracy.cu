@@ -1,4 +1,4 @@
-// Accuracy check of the replay-tier math helpers (frcp/fdiv/fsqrt/frsqrt/flog in csrc/ptl_physics.cuh) against the
+// Accuracy check of the replay-tier math helpers (frcp/fdiv/fsqrt/frsqrt/flog/fsincospi in csrc/ptl_physics.cuh) against the
 // correctly-rounded / libdevice results, in ulps, over 2^24 random arguments per function.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -I particulator.jl_b200/csrc -I include scripts/math_accuracy.cu -o /tmp/math_accuracy
 #include <cstdio>
@@ -31,13 +31,19 @@ __device__ double rnd_arg(uint32_t i, int mode) {
 __global__ void k_check(int mode, double* maxerr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     double x = rnd_arg(i, mode);
-    double e[5];
+    double e[7];
     e[0] = ulps(ptl::flog(x), log(x));
     e[1] = ulps(ptl::frsqrt(x), rsqrt(x));
     e[2] = ulps(ptl::fsqrt(x), sqrt(x));
     e[3] = ulps(ptl::frcp(x), 1.0 / x);
     e[4] = ulps(ptl::fdiv(0.7310585786300049, x), 0.7310585786300049 / x);
-    for (int k = 0; k < 5; k++) {
+    {
+        double sr, cr, sf, cf, xx = mode == 0 ? 2 * x : (mode == 2 ? x : 2 * rnd_arg(i, 0) * (i & 1 ? 1.0 : 1e-3));
+        sincospi(xx, &sr, &cr);
+        ptl::fsincospi(xx, sf, cf);
+        e[5] = ulps(sf, sr); e[6] = ulps(cf, cr);
+    }
+    for (int k = 0; k < 7; k++) {
         double m = e[k];
         for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
         if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)&maxerr[k], (unsigned long long)__double_as_longlong(m));
@@ -46,17 +52,17 @@ __global__ void k_check(int mode, double* maxerr) {
 
 int main() {
     double* d;
-    cudaMalloc(&d, 5 * sizeof(double));
-    const char* names[5] = {"flog", "frsqrt", "fsqrt", "frcp", "fdiv"};
+    cudaMalloc(&d, 7 * sizeof(double));
+    const char* names[7] = {"flog", "frsqrt", "fsqrt", "frcp", "fdiv", "sinpi", "cospi"};
     const char* modes[4] = {"u in (0,1)", "1e-43..1e43", "1 +- 5e-4", "2^-20..2^20"};
     int bad = 0;
     for (int mode = 0; mode < 4; mode++) {
-        cudaMemset(d, 0, 5 * sizeof(double));
+        cudaMemset(d, 0, 7 * sizeof(double));
         k_check<<<(1 << 24) / 256, 256>>>(mode, d);
-        double h[5];
+        double h[7];
         if (cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { printf("CUDA error\n"); return 2; }
         printf("%-12s", modes[mode]);
-        for (int k = 0; k < 5; k++) { printf("  %s %.3f ulp", names[k], h[k]); if (!(h[k] <= 2.0)) bad = 1; }
+        for (int k = 0; k < 7; k++) { printf("  %s %.3f ulp", names[k], h[k]); if (!(h[k] <= 2.0)) bad = 1; }
         printf("\n");
     }
     printf(bad ? "FAIL (> 2 ulp)\n" : "OK (all <= 2 ulp)\n");
