@@ -15,6 +15,7 @@ from .tables import (ChebyshevCollisionTable, CollisionTable, collision_table_fr
                      air_composition, build_electron_collision_table, build_positron_collision_table,
                      build_photon_collision_table, synthetic_lxcat_table, lxcat_table_from_rates, loglinrange)
 from . import seltzer
+from .lxcat import load_lxcat, lxcat_collision_table, ensure_elastic
 from ._lib import PtlError, Backend, cuda_backend, LIB_PATH, ABI_SYMBOLS
 from .context import Context
 from .field import (ZeroField, HomogeneousField, DoubleLayerField, StepField, ConfinedDoubleLayerField,
@@ -28,5 +29,7 @@ from .mixed_population import MultiPopulation, init, advance, last_advance_stats
 from .callback import (AbstractCallback, VoidCallback, CombinedCallback, CollisionCounter, WallCallback,
                        ParticleCountCallback, RouletteCallback, SplitCallback, PopulationTargetCallback)
 from .run import run
+from . import checkpoint
+from .checkpoint import save_checkpoint, load_checkpoint, read_checkpoint
 
 Electron, Photon, Positron, SlowElectron = ELECTRON, PHOTON, POSITRON, SLOW_ELECTRON

@@ -152,9 +152,27 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
         }
 
         // ---- execute this warp's chunks ----
+        // Static assignment (chunk = wid + cw * BQ_WARPS).  Measured alternative, -DBQ_DYNAMIC_CHUNKS: warps claim plan
+        // indices from a shared counter so that a warp which drew short units takes the next chunk instead of waiting at
+        // the barrier (the wait is 21 % of the warp samples, profiles/r1_s2_bq_hotspots.md).  On B200 it is 2 % SLOWER
+        // (36.7 vs 35.9 ms, 4e6 electrons): the second CTA of the SM already fills the barrier wait, and the claim adds
+        // an atomic + shuffle per chunk.  Kept as a documented negative result.  Also measured: two consecutive plan
+        // entries per warp (chunk = wid * BQ_CPW + cw; mostly one class per warp, warmer instruction cache) 17 % slower
+        // (41.4 ms: a warp with two STEP chunks holds the barrier); pairing first with last (w, 15 - w) +0.5 %, within noise.
+#ifndef BQ_DYNAMIC_CHUNKS
 #pragma unroll 1
         for (int cw = 0; cw < BQ_CPW; cw++) {
             const int chunk = wid + cw * BQ_WARPS;               // index in the plan order
+#else
+        const int nplan = nfull + __popc(__ballot_sync(0xffffffffu, part_c));
+        unsigned int* claim = cnt + 8 * cb3 + 6;                 // unused entry of this round's counter row (zeroed two rounds ago)
+#pragma unroll 1
+        for (;;) {
+            int chunk = 0;
+            if (lane == 0) chunk = (int)atomicAdd(claim, 1u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk >= nplan) break;
+#endif
             const unsigned mfull = __ballot_sync(0xffffffffu, lane < BQ_NCLASS && chunk >= start_c && chunk < start_c + f_c);
             const unsigned mpart = __ballot_sync(0xffffffffu, part_c && rk_c == chunk - nfull);
             const unsigned msel = mfull ? mfull : mpart;

@@ -333,6 +333,39 @@ def test_slow_electron_replay(gctx, octx):
     assert bad.sum() <= max(2, 0.002 * len(common)), int(bad.sum())
 
 
+def test_lxcat_json_table_replay(gctx, octx, tmp_path):
+    """A table built by `load_lxcat` from a JSON database (EFFECTIVE->ELASTIC, 3-body attachment, rescale) drives the
+    same kernels: deterministic replay against the oracle."""
+    import lxcat_fixture
+    f = lxcat_fixture.write(str(tmp_path / "air.json"))
+    tab = P.lxcat_collision_table(f, {"N2": 0.79 * co.nair, "O2": 0.21 * co.nair}, nE=2048, emax=100 * co.eV)
+    n = 4000
+    rng = np.random.default_rng(11)
+    st = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * co.eV / co.electron_mass) * 1.5,
+              s=-np.log(1 - rng.random(n)), uid=np.arange(1, n + 1, dtype=np.uint64))
+    E = 150 * co.Td * co.nair
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -E]), None))
+    pops = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(5, 0)
+        pop = P.Population(ctx, P.SLOW_ELECTRON, 4 * n, st, tab, 0.0)
+        mp = P.MultiPopulation(("slow", pop))
+        t = 0.0
+        for _ in range(3):
+            t += 1e-12
+            P.advance(mp, psh, t)
+        pops.append((pop, P.last_advance_stats(mp)))
+    (pg, sg), (po_, so) = pops
+    assert abs(sg["substeps"] - so["substeps"]) <= 2e-3 * so["substeps"] + 20
+    g, o = _by_uid(pg), _by_uid(po_)
+    common, ig, io = np.intersect1d(g["uid"], o["uid"], return_indices=True)
+    assert len(common) >= 0.998 * max(len(g["uid"]), len(o["uid"]))
+    vs = np.maximum(np.linalg.norm(o["p"][io], axis=1), 1e3)[:, None]
+    bad = (np.abs(g["p"][ig] - o["p"][io]) / vs).max(axis=1) > REPLAY_RTOL
+    bad |= g["active"][ig] != o["active"][io]
+    assert bad.sum() <= max(2, 0.002 * len(common)), int(bad.sum())
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at larger sizes (no oracle)
 # ---------------------------------------------------------------------------------------------------
