@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(AQ_THREADS, 2) k_advance_aq(const __grid_const
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) {
                 int i = q / WF_CUM_STRIDE, rr = q - i * WF_CUM_STRIDE;
                 int j = rr & 15, m = rr >> 4;
-                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
+                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? WF_CUM_PAD : 0.0);
             }
         } else {
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) tsm[q] = T.cum[q];

@@ -27,6 +27,11 @@ constexpr int WF_WARPS = WF_THREADS / 32;
 enum { WS_LOAD = 0, WS_STEP, WS_COULOMB, WS_RBEB, WS_IONFIN, WS_OTHER, WS_IDLE, WS_NCLASS };
 static_assert(WS_IDLE == 6 && WF_WARPS == 8, "the lane-parallel scheduler assumes 6 work classes x 8 warps");
 constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the shared-memory cumulative-rate table
+#ifdef WF_LINEAR_SELECT
+#define WF_CUM_PAD (-INFINITY)           // full scan: padded processes never win
+#else
+#define WF_CUM_PAD INFINITY              // binary search: padded processes sort last
+#endif
 constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
 constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 constexpr uint32_t WF_COAST = 0x400u;   // OTHER unit: no collision, take the repeated below-cut sub-steps in blocks
@@ -158,6 +163,29 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
     int jsel = -1;
     bool nearb = false;
     const double guard = 1e-9 * r;
+#ifndef WF_LINEAR_SELECT
+    if (TK == 0 && FAST) {
+        // Binary search over the running sums.  On an interval where every fitted rate is non-negative (T.mono_mask, checked
+        // on the host at table upload) cum_0 <= cum_1 <= ... up to rounding, so "first j with cum_j > xi0" is a lower-bound
+        // search: four probes instead of 16 evaluations, then the two entries that bracket xi0 are checked against the guard
+        // band -- any disagreement with the reference's sequential subtraction needs one of those two within rounding of xi0.
+        // Layout [interval][m][16], padded with +inf (sorts last); np <= 16.
+        const double* c = cum + WF_CUM_STRIDE * pre.i;
+        const double ca = pre.a, cb = pre.b;
+#define WF_CUMJ(j) fma(c[32 + (j)], cb, fma(c[16 + (j)], ca, c[(j)]))
+        int j = !(WF_CUMJ(7) > xi0) ? 8 : 0;
+        j += !(WF_CUMJ(j + 3) > xi0) ? 4 : 0;
+        j += !(WF_CUMJ(j + 1) > xi0) ? 2 : 0;
+        j += !(WF_CUMJ(j) > xi0) ? 1 : 0;                       // entries 0..14 examined: j = how many are <= xi0
+        double dj = WF_CUMJ(j) - xi0;                            // j == 15: the 16th entry (a process or the +inf pad)
+        if (np > 15 && j == 15 && !(dj > 0)) j = 16;
+        const double dp = WF_CUMJ(j > 0 ? j - 1 : 0) - xi0;
+        if (j == 16) dj = INFINITY;
+        nearb = (fabs(dj) < guard) | (fabs(dp) < guard) | !((T.mono_mask >> pre.i) & 1ULL);
+        jsel = j < np ? j : -1;
+#undef WF_CUMJ
+    } else if (TK == 0) {
+#else
     if (TK == 0 && FAST) {
         // shared-memory layout [interval][m][16] (order 3, <= 16 processes, padded with -inf): two processes per LDS.128.
         // Interval stride WF_CUM_STRIDE = 50 doubles (400 B = 4 banks mod 32): lanes in different energy intervals hit
@@ -174,6 +202,7 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
             jsel = (jsel < 0 && d1 > 0) ? 2 * j2 + 1 : jsel;
         }
     } else if (TK == 0) {
+#endif
         const double* c = cum + T.order * np * pre.i;
         for (int j = 0; j < np; j++) {
             const double* a = c + T.order * j;
@@ -481,7 +510,7 @@ __global__ void __launch_bounds__(WF_THREADS, WF_MIN_BLOCKS) k_advance_wf(const 
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) {
                 int i = q / WF_CUM_STRIDE, rr = q - i * WF_CUM_STRIDE;
                 int j = rr & 15, m = rr >> 4;
-                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? -INFINITY : 0.0);
+                tsm[q] = (m < 3 && j < T.nprocs) ? T.cum[m + 3 * (j + T.nprocs * i)] : (m == 0 ? WF_CUM_PAD : 0.0);
             }
         } else {
             for (int q = threadIdx.x; q < nrate; q += blockDim.x) tsm[q] = T.cum[q];

@@ -548,6 +548,22 @@ EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t np
         rc = upload_doubles(ctx, cum.data(), cum.size(), &T.d_cum); if (rc) return rc;
         T.v.cum = T.d_cum;
     }
+    // Intervals on which no fitted rate dips below zero (fits do near process thresholds): exact minimum of
+    // a0 + a1 x + a2 (2 x^2 - 1) over [-1, 1].  There the running sums are non-decreasing in the process index and the
+    // kernels may select by binary search; elsewhere they scan sequentially like the reference.
+    T.v.mono_mask = 0;
+    if (order == 3 && k + 1 <= 64) {
+        for (int i = 0; i <= k; i++) {
+            bool ok = true;
+            for (int j = 0; j < nprocs && ok; j++) {
+                const double* a = rate + (size_t)order * ((size_t)j + (size_t)nprocs * i);
+                double mn = fmin(a[0] - a[1] + a[2], a[0] + a[1] + a[2]);
+                if (a[2] > 0 && fabs(a[1]) <= 4 * a[2]) { double x = -a[1] / (4 * a[2]); mn = fmin(mn, a[0] + a[1] * x + a[2] * (2 * x * x - 1)); }
+                ok = mn >= 0;      // NaN -> false
+            }
+            if (ok) T.v.mono_mask |= 1ULL << i;
+        }
+    }
     rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
     T.smem_bytes = sizeof(double) * ((size_t)order * nprocs * (k + 1) + (size_t)order * (k + 1)) + sizeof(ptl_process_desc) * nprocs;
     if (T.smem_bytes > 60 * 1024) { ctx->err = "Chebyshev table too large for shared memory"; return PTL_EINVAL; }

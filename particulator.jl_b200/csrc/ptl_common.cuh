@@ -59,6 +59,8 @@ struct TableView {
     double L1, L2, maxrate;
     const ptl_process_desc* procs;   // device copy
     unsigned long long* counts;      // [nprocs + 1]
+    unsigned long long mono_mask;    // cheb, order 3: bit i set <=> every fitted rate is >= 0 on interval i, so the running
+                                     // sums over processes are non-decreasing there (binary-search selection is valid)
 };
 
 struct SbView {
