@@ -56,7 +56,7 @@ template <int SP>
 __device__ __forceinline__ double own_ratebound(const AdvanceParams& P, const SmemTable& S, double eng) {
     const TableView& T = P.tab[SP];
     if (T.kind == 0) {
-        Pre pre = precheb(eng, T.k, T.xmax);
+        Pre pre = precheb(eng, T.k, T.xmax, T.rxmax);
         if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
         return chebsum(S.ratebound + T.order * pre.i, pre, T.order);
     }
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
             if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
                 double eng;
                 if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {   // :148-151
-                    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
+                    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax, T.rxmax) : indweight(T, eng);   // :153
                     if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
                     rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
                     double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;                     // :154
@@ -347,7 +347,7 @@ __global__ void k_table_eval(TableView T, long long n, const double* __restrict_
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double eng = energy[i];
-    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);
+    Pre pre = (T.kind == 0) ? precheb(eng, T.k, T.xmax, T.rxmax) : indweight(T, eng);
     for (int j = 0; j < T.nprocs; j++)
         rates[j + (size_t)T.nprocs * i] = (T.kind == 0) ? chebsum(T.rate + (size_t)T.order * (j + (size_t)T.nprocs * pre.i), pre, T.order)
                                                         : linear_rate(T.rate, T.nprocs, j, pre);

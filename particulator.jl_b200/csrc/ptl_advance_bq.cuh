@@ -29,7 +29,12 @@ constexpr int BQ_WARPS = BQ_THREADS / 32;
 #define BQ_PART_MIN 28
 #endif
 constexpr int BQ_CPW = BQ_CPW_MACRO;               // chunks per warp and round
+#ifdef BQ_SLOTS_MACRO
+constexpr int BQ_SLOTS = BQ_SLOTS_MACRO;            // may be below the chunk capacity (then not every chunk slot is used)
+#else
 constexpr int BQ_SLOTS = BQ_THREADS * BQ_CPW;
+#endif
+static_assert(BQ_SLOTS <= BQ_THREADS * BQ_CPW && BQ_SLOTS % 32 == 0, "the plan executes at most BQ_CHUNKS full chunks per round");
 constexpr int BQ_NCLASS = WS_IDLE;                 // 6 lists
 constexpr int BQ_CHUNKS = BQ_WARPS * BQ_CPW;       // chunks executed per round
 

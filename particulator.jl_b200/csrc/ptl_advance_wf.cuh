@@ -113,11 +113,25 @@ __device__ __noinline__ unsigned long long wf_coast_below_cut(const AdvanceParam
 }
 
 // after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP
+// setr! for the common table shape (Chebyshev, order 3), inline on the shared-memory rate-bound rows: ~55 instructions.
+// The generic setr<SP> is an out-of-line call that reads AdvanceParams through a generic pointer and carries the
+// any-order loop and the IEEE-division fallback (112 executed instructions per call, 6 % of the kernel in ncu).
 template <int SP>
-__device__ __forceinline__ void wf_after_collision(const AdvanceParams& P, const SmemTable& T, const WfPool& S, int it, Vec3 p, double s) {
+__device__ __forceinline__ double wf_setr_cheb3(const AdvanceParams& P, const TableView& T, const double* __restrict__ rb, double cut, Vec3 p) {
+    const double eng = kinenergy<SP>(p);
+    if (eng < cut) return 0.0;                                                         // collisions.jl:66
+    const Pre pre = precheb(eng, T.k, T.xmax, T.rxmax);
+    if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+    const double* a = rb + 3 * pre.i;
+    return __dadd_rn(__dadd_rn(a[0], __dmul_rn(a[1], pre.a)), __dmul_rn(a[2], pre.b));   // chebsum, order 3
+}
+
+template <int SP>
+__device__ __forceinline__ void wf_after_collision(const AdvanceParams& P, const SmemTable& T, const WfPool& S, int it, Vec3 p, double s,
+                                                   const bool cheb3 = false, const double cut = 0.0) {
     wf_put3(S, WD_P0, it, p);
     WFD(WD_S, it) = s;
-    WFD(WD_R, it) = setr<SP>(P, T, p);
+    WFD(WD_R, it) = cheb3 ? wf_setr_cheb3<SP>(P, P.tab[SP], T.ratebound, cut, p) : setr<SP>(P, T, p);
     S.state[it] = WS_STEP | WF_VALID;
 }
 
@@ -272,7 +286,8 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         double t = Q.col[COL_T][i];
         wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
         WFD(WD_T, it) = t; WFD(WD_S, it) = Q.col[COL_S][i];
-        WFD(WD_R, it) = FIRST ? setr<SP>(P, TS, p) : Q.col[COL_R][i];     // advance_init!  mixed_population.jl:97-110
+        WFD(WD_R, it) = FIRST ? (fastsel ? wf_setr_cheb3<SP>(P, T, TS.ratebound, cut, p) : setr<SP>(P, TS, p))
+                              : Q.col[COL_R][i];                           // advance_init!  mixed_population.jl:97-110
         WFD(WD_TREM, it) = P.tfinal - t;                                   // :65
         S.uid[it] = Q.uid[i]; S.row[it] = i;
         S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
@@ -289,6 +304,23 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         bool collides = trem > tnext;                   // :68
         double dt = collides ? tnext : trem;
         if (!collides) s -= dt * r;                     // :74
+        // Speculative draws (no in-loop callbacks): the Philox block of this sub-step's collision test depends only on the
+        // slot's RNG cursor and the null outcome's s = -log(u2) only on that block, so both are computed HERE, inline, where
+        // their ~220 cycles of dependent integer / polynomial latency overlap the push, the energy and the table search
+        // instead of following them through two out-of-line calls.  The warp executed both anyway whenever one lane had a
+        // null event.  The cursor is committed only if the test really draws (same stream, same values as rng.u()).
+        uint32_t sp_idx = 0, sp_o2 = 0, sp_o3 = 0;
+        double sp_u1 = 0.0, sp_snull = 0.0;
+        if (!CB) {
+            const unsigned long long uid = S.uid[it];
+            const uint32_t ic = S.idx[it];
+            sp_idx = ic + (ic & 1u);                    // every collision test starts on an even draw index
+            uint32_t o4[4];
+            philox4x32_10(sp_idx >> 1, rc.step, rc.seed_lo, rc.seed_hi, (uint32_t)uid, (uint32_t)(uid >> 32) ^ DOM_COLLISION, o4);
+            sp_u1 = bits_to_u01(o4[0], o4[1]);
+            sp_snull = -flog_u01(bits_to_u01(o4[2], o4[3]));
+            sp_o2 = o4[2]; sp_o3 = o4[3];
+        }
         Vec3 xo = x, po = p;
         double to = t;
         push<SP>(P, x, p, t, dt);                       // :77
@@ -328,11 +360,16 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         if (collides && act) {                          // :83  do_one_collision!  collisions.jl:142-199
             double eng;
             if (r != 0.0 && (eng = kinenergy<SP>(p)) >= cut) {                     // :148-151
-                Pre pre = (TK == 0) ? precheb(eng, T.k, T.xmax) : indweight(T, eng);   // :153
+                Pre pre = (TK == 0) ? precheb(eng, T.k, T.xmax, T.rxmax) : indweight(T, eng);   // :153
                 if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
-                if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
-                rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
-                double xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;             // :154
+                double xi;
+                if (CB) {
+                    if (!rng_loaded) { wf_load_rng(S, it, rng); rng_loaded = true; }
+                    rng.idx += rng.idx & 1u;   // every collision test starts on an even draw index (Philox block boundary)
+                    xi = rng.u(rc.step, rc.seed_lo, rc.seed_hi) * r;                // :154
+                } else {
+                    xi = sp_u1 * r;
+                }
                 const int np = T.nprocs;
                 bool rbv;
                 int jsel;                                                                   // :166-180
@@ -349,8 +386,16 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                 if (kind == PTL_PROC_NULL) {            // NullOutcome: setr! then s = nextcoll()  (:83-88, :182-196)
                     // setr! recomputes kinenergy and presample from the same p: reuse them
                     r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : T.maxrate;
-                    s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                    if (CB) {
+                        s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+                    } else {
+                        s = sp_snull;
+                        S.idx[it] = sp_idx + 2;         // both halves of the block consumed: nothing to cache
+                    }
                 } else {
+                    if (!CB) {                          // xi consumed; the second half of the block stays cached for the sampler
+                        S.idx[it] = sp_idx + 1; S.cblock[it] = sp_idx >> 1; S.c2[it] = sp_o2; S.c3[it] = sp_o3;
+                    }
                     WFD(WD_ENG, it) = eng;
                     uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
                     next = c | WF_VALID | ((uint32_t)jsel << 16);
@@ -373,7 +418,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         Outcome o;
         collide_coulomb<SP>(rng, rc, TS.procs[sw >> 16], p, o);
         wf_store_rng(S, it, rng);
-        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
         break;
     }
     // ------------------------------------------------------------------------------------------
@@ -415,7 +460,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         const double ccut = P.pop[PTL_ELECTRON].present ? P.pop[PTL_ELECTRON].energy_cut : INFINITY;
         ionization_products(rng, rc, p, eng, E1, E2, o, ccut);
         wf_store_rng(S, it, rng);
-        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
         if (o.sp2 >= 0) {
             uint64_t cu[2];
             child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
@@ -426,6 +471,8 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
     }
     // ------------------------------------------------------------------------------------------
     case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
+        // (moving this unit out of line to keep the hot units' code contiguous was measured 4.6 % SLOWER: passing the pool
+        // by reference to a real function keeps its pointers live in registers across the whole kernel)
         if (sw & WF_COAST) {
             nsub += wf_coast_below_cut<SP>(P, S, it, cut);
             break;
@@ -447,10 +494,10 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
             S.state[it] = WS_STEP | WF_VALID;
             break;
         case OUT_STATE_CHANGE:
-            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
             break;
         case OUT_NEW_PARTICLE:
-            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1);
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
             child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
             add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
             break;

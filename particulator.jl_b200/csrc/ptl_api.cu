@@ -530,7 +530,7 @@ EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t np
                                      const double* ratebound, const ptl_process_desc* procs) {
     if (!ctx || order < 1 || order > MAX_ORDER || nprocs < 0 || nprocs > PTL_MAX_PROCS || k < 1 || !(xmax > 0)) return PTL_EINVAL;
     Table T;
-    T.v.kind = 0; T.v.order = order; T.v.k = k; T.v.xmax = xmax;
+    T.v.kind = 0; T.v.order = order; T.v.k = k; T.v.xmax = xmax; T.v.rxmax = 1.0 / xmax;
     int32_t rc = upload_doubles(ctx, rate, (size_t)order * nprocs * (k + 1), &T.d_rate); if (rc) return rc;
     rc = upload_doubles(ctx, ratebound, (size_t)order * (k + 1), &T.d_rb); if (rc) return rc;
     T.v.rate = T.d_rate; T.v.ratebound = T.d_rb;
@@ -597,7 +597,7 @@ EXPORT int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, 
     if (!ctx || order < 1 || order > MAX_ORDER || k < 1) return PTL_EINVAL;
     if (ctx->cls.size() >= (size_t)MAX_CHEBLOSS) return PTL_ENOMEM;
     ChebLoss c;
-    c.v.order = order; c.v.k = k; c.v.xmax = xmax;
+    c.v.order = order; c.v.k = k; c.v.xmax = xmax; c.v.rxmax = 1.0 / xmax;
     double *de = nullptr, *dp = nullptr;
     int32_t rc = upload_doubles(ctx, ec, (size_t)order * (k + 1), &de); if (rc) return rc;
     rc = upload_doubles(ctx, pc, (size_t)order * (k + 1), &dp); if (rc) return rc;

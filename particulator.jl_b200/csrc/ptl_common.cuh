@@ -52,6 +52,7 @@ struct TableView {
     int nprocs;
     int order, k;
     double xmax;
+    double rxmax;                    // RN(1 / xmax), host-computed: precheb divides by Markstein's exact sequence
     const double* rate;              // cheb: [order, nprocs, k+1]; linear: [nprocs, nE]
     const double* ratebound;         // cheb: [order, k+1]
     const double* cum;               // running sum over processes of `rate` (same layout): selection accelerator
@@ -72,6 +73,7 @@ struct SbView {
 struct ChebLossView {
     int order, k;
     double xmax;
+    double rxmax;
     const double* ec;
     const double* pc;
 };
