@@ -109,6 +109,10 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
         const unsigned short* lcur = lists + (round & 1) * (BQ_NCLASS * BQ_SLOTS);
         unsigned short* lnxt = lists + ((round & 1) ^ 1) * (BQ_NCLASS * BQ_SLOTS);
         if (tid < 8) cold[tid] = 0;
+#ifdef BQ_PROFILE
+        const long long pr_t0 = clock64();
+        long long pr_umax = 0;
+#endif
 
         // ---- chunk plan, computed once per warp with lane c holding class c ----
         // full chunks in class order, then the largest remainders (ties -> lower class) while chunks are left
@@ -143,6 +147,8 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
             const int rd = __shfl_sync(0xffffffffu, r_c, d);
             rk_c += (rd > r_c) || (rd == r_c && d < lane);
         }
+        // (A pool larger than one round executes -- 544..608 slots for 16 chunk slots, so that every round finds 16 full
+        // chunks -- was measured 3-6 % slower: the carry-over copies grow with the waiting entries.)
         const int npartial = BQ_CHUNKS - nfull;                  // nfull <= BQ_CHUNKS because the pool has BQ_CHUNKS*32 slots
         // While the pool is busy (at least half of the chunk slots are full chunks) a remainder below BQ_PART_MIN lanes waits
         // and grows instead of costing a whole warp pass for a few lanes (+0.7 %; RBEB/IONFIN chunks ran at 14-17 lanes).
@@ -197,6 +203,9 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
             }
             const bool has = it >= 0;
             const unsigned amask = __ballot_sync(0xffffffffu, has);
+#ifdef BQ_PROFILE
+            const long long pr_u0 = clock64();
+#endif
             if (has) {
                 const uint32_t sw = S.state[it];
                 wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, amask, lane, ltmask, row_counter, i0, i1, nsub, rows);
@@ -212,8 +221,28 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
                 }
             }
             __syncwarp();
+#ifdef BQ_PROFILE
+            if (msel) {
+                const long long du = clock64() - pr_u0;
+                pr_umax = du > pr_umax ? du : pr_umax;
+                if (lane == 0) {
+                    const int pc = __ffs(msel) - 1;
+                    atomicAdd(P.dbg + 16 + pc, (unsigned long long)du); atomicAdd(P.dbg + 24 + pc, 1ULL); atomicMax(P.dbg + 32 + pc, (unsigned long long)du);
+                }
+            }
+#endif
         }
+#ifdef BQ_PROFILE
+        const long long pr_b0 = clock64();
+#endif
         __syncthreads();
+#ifdef BQ_PROFILE
+        if (lane == 0) {
+            const long long pr_t1 = clock64();
+            atomicAdd(P.dbg + 40, (unsigned long long)(pr_t1 - pr_b0)); atomicAdd(P.dbg + 41, 1ULL);
+            atomicAdd(P.dbg + 42, (unsigned long long)(pr_t1 - pr_t0)); atomicAdd(P.dbg + 43, (unsigned long long)pr_umax);
+        }
+#endif
     }
 
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);

@@ -32,6 +32,9 @@ constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the s
 #else
 #define WF_CUM_PAD INFINITY              // binary search: padded processes sort last
 #endif
+#ifndef WF_RBEB_TRIALS
+#define WF_RBEB_TRIALS 0                 // rejection trials evaluated side by side per RBEB unit (0: the sequential two-trial loop)
+#endif
 constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
 constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 constexpr uint32_t WF_COAST = 0x400u;   // OTHER unit: no collision, take the repeated below-cut sub-steps in blocks
@@ -422,7 +425,47 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         break;
     }
     // ------------------------------------------------------------------------------------------
-    case WS_RBEB: {   // rejection trials of rbeb.jl:170-196, two per unit
+    case WS_RBEB: {   // rejection trials of rbeb.jl:170-196, WF_RBEB_TRIALS per unit
+#if WF_RBEB_TRIALS > 0
+        // Trial q of the reference's loop consumes draws (2q, 2q+1) after the cursor whatever the earlier trials decided,
+        // so the trials of one unit are independent: their Philox blocks and acceptance tests are evaluated side by side
+        // (instruction-level parallelism instead of call -> test -> call -> test), the FIRST accepted one wins and the
+        // cursor advances only past the draws the sequential loop would have consumed.  Same stream, same values.
+        constexpr int NT = WF_RBEB_TRIALS;
+        const unsigned long long uid = S.uid[it];
+        const uint32_t k0 = (uint32_t)uid, k1 = (uint32_t)(uid >> 32) ^ DOM_COLLISION;
+        const uint32_t idx0 = S.idx[it], b0 = idx0 >> 1;
+        const bool po = (idx0 & 1u) != 0;
+        uint32_t bw[NT + 1][4];
+        if (po && S.cblock[it] == b0) { bw[0][0] = 0; bw[0][1] = 0; bw[0][2] = S.c2[it]; bw[0][3] = S.c3[it]; }
+        else philox4x32_10(b0, rc.step, rc.seed_lo, rc.seed_hi, k0, k1, bw[0]);
+#pragma unroll
+        for (int m = 1; m <= NT; m++) philox4x32_10(b0 + m, rc.step, rc.seed_lo, rc.seed_hi, k0, k1, bw[m]);
+        double eng = WFD(WD_ENG, it);
+        double B = TS.procs[sw >> 16].par[0];
+        RbebConsts k = rbeb_consts<true>(eng, B);
+        double w = 0.0;
+        int qacc = -1;
+#pragma unroll
+        for (int q = NT - 1; q >= 0; q--) {           // descending: the lowest accepted q is written last
+            const int j0 = 2 * q, j1 = 2 * q + 1;       // draw j sits in block (po + j) >> 1, half (po + j) & 1
+            const double u = bits_to_u01(po ? bw[(1 + j0) >> 1][2 * ((1 + j0) & 1)] : bw[j0 >> 1][2 * (j0 & 1)],
+                                         po ? bw[(1 + j0) >> 1][2 * ((1 + j0) & 1) + 1] : bw[j0 >> 1][2 * (j0 & 1) + 1]);
+            const double u2 = bits_to_u01(po ? bw[(1 + j1) >> 1][2 * ((1 + j1) & 1)] : bw[j1 >> 1][2 * (j1 & 1)],
+                                          po ? bw[(1 + j1) >> 1][2 * ((1 + j1) & 1) + 1] : bw[j1 >> 1][2 * (j1 & 1) + 1]);
+            double wq;
+            if (rbeb_trial(k, u, u2, wq)) { qacc = q; w = wq; }
+        }
+        const bool acc = qacc >= 0;
+        {
+            const uint32_t idx = idx0 + (acc ? 2u * (uint32_t)(qacc + 1) : 2u * NT);
+            const uint32_t cb = idx >> 1;               // block holding the next draw: b0 + 1 .. b0 + NT
+            uint32_t c2 = bw[NT][2], c3 = bw[NT][3];
+#pragma unroll
+            for (int m = NT - 1; m >= 1; m--) if (cb - b0 == (uint32_t)m) { c2 = bw[m][2]; c3 = bw[m][3]; }
+            S.idx[it] = idx; S.cblock[it] = cb; S.c2[it] = c2; S.c3[it] = c3;
+        }
+#else
         Rng rng;
         wf_load_rng(S, it, rng);
         double eng = WFD(WD_ENG, it);
@@ -437,7 +480,8 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
             acc = rbeb_trial(k, u, u2, w);
         }
         wf_store_rng(S, it, rng);
-        if (!acc) break;                  // stays an RBEB item: two more trials next round
+#endif
+        if (!acc) break;                  // stays an RBEB item: more trials next round
         WFD(WD_SCR, it) = B * w;          // E2
 #ifdef WF_SPLIT_IONFIN
         S.state[it] = WS_IONFIN | WF_VALID | (sw & 0xffff0000u);

@@ -31,7 +31,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
     unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[DIAG_NVAL];
-    unsigned long long dbg[16];    // PTL_TRACE: max / sum of scheduler rounds per CTA, CTA count
+    unsigned long long dbg[64];    // PTL_TRACE: max / sum of scheduler rounds per CTA, CTA count
 };
 
 struct Table {
@@ -1043,6 +1043,18 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
                 fprintf(stderr, "[ptl trace]     lonely rounds by class: %llu %llu %llu %llu %llu %llu; last lonely row %llu p=(%.4e %.4e %.4e) r=%.4e s=%.4e\n",
                         g[4], g[5], g[6], g[7], g[8], g[9], g[3], v[0], v[1], v[2], v[3], v[4]);
             }
+#ifdef BQ_PROFILE
+            if (ctx->stats.passes > 0 && ctx->h_sc->dbg[2]) {   // per-class chunk timing (clock64) of the list-scheduled kernel
+                const unsigned long long* g = ctx->h_sc->dbg;
+                static const char* nm[6] = {"LOAD", "STEP", "COULOMB", "RBEB", "IONFIN", "OTHER"};
+                for (int c = 0; c < 6; c++)
+                    if (g[24 + c]) fprintf(stderr, "[ptl trace]     %-8s chunks %10llu  mean %7.0f cyc  max %8llu cyc  share %5.1f %%\n", nm[c], g[24 + c],
+                                           (double)g[16 + c] / (double)g[24 + c], g[32 + c], 100.0 * (double)g[16 + c] / (double)(g[42] ? g[42] : 1));
+                fprintf(stderr, "[ptl trace]     rounds %llu: warp-cycles total %.3e, in units %.1f %%, at the barrier %.1f %%, max unit per round mean %.0f cyc, round mean %.0f cyc\n",
+                        g[41] / 8, (double)g[42], 100.0 * (double)(g[16] + g[17] + g[18] + g[19] + g[20] + g[21]) / (double)(g[42] ? g[42] : 1),
+                        100.0 * (double)g[40] / (double)(g[42] ? g[42] : 1), (double)g[43] / (double)(g[41] ? g[41] : 1) , (double)g[42] / (double)(g[41] ? g[41] : 1));
+            }
+#endif
             CK(cudaMemsetAsync(ctx->d_sc->dbg, 0, sizeof(ctx->d_sc->dbg), ctx->stream));
             tprev = tnow; sub_prev = sub;
         }
