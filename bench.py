@@ -105,30 +105,51 @@ def pusher(P):
     return P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -EFIELD]), P.HomogeneousField([0.0, 0.0, 0.0])))
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line): ONE
+    `nvidia-smi -lms 200` process started before and killed after, as the recipe says.  (Spawning a fresh nvidia-smi every
+    200 ms re-initialises NVML each time and stalled the CUDA calls of the pass loop: the non-kernel part of a step varied
+    between 100 and 290 ms from box to box.)"""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, 0.0
 
-    def run(self):
-        while not self._halt.is_set():
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def _collect(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([v.strip() for v in out.split(",")])
+                self.proc.kill()
+                out, _ = self.proc.communicate(timeout=5)
             except Exception:
-                pass
-            self._halt.wait(0.2)
+                out = ""
+        import datetime
+        for line in (out or "").splitlines():
+            if not line.strip():
+                continue
+            r = [v.strip() for v in line.split(",")]
+            try:                   # timestamp: YYYY/MM/DD HH:MM:SS.mmm (local time)
+                ts = datetime.datetime.strptime(r[-1], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = None
+            if ts is None or ts >= self.t_begin - 0.05:
+                self.rows.append(r)
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
+        self._collect()
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -258,27 +279,36 @@ def main():
 
     t = 0.0
 
+    host_ms = {"advance": [], "droplow": []}     # host wall time of the two calls (both end in a scalar read-back)
+
     def step():
         nonlocal t
         n0 = len(el)
         t += DT
+        h0 = time.perf_counter()
         P.advance(mp, psh, t)
+        h1 = time.perf_counter()
         st = P.last_advance_stats(mp)
         for q in mp:
             P.droplow(q)
+        h2 = time.perf_counter()
+        host_ms["advance"].append((h1 - h0) * 1e3)
+        host_ms["droplow"].append((h2 - h1) * 1e3)
         return n0, st
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # started before the warm-up so that its NVML initialisation is over when the timing starts
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.t_begin = time.time()  # only samples taken inside the timed region are reported
     ctx.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     psteps = substeps = 0
     main_ms = main_rows = 0.0
+    host_ms["advance"].clear(); host_ms["droplow"].clear()
     for _ in range(args.steps):
         n0, st = step()
         psteps += n0
@@ -287,6 +317,7 @@ def main():
         main_rows += st["main_rows"]
     e1.record()
     barrier()
+    host_steps = {k: [round(v, 1) for v in vals] for k, vals in host_ms.items()}
     elapsed_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -424,7 +455,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
                 "kappa": substeps_all / max(psteps_all, 1.0), "substeps_per_s": substeps_all / (elapsed_all * 1e-3),
-                "hbm_roofline_frac_whole_step": (ALGO_BYTES_PER_PARTICLE_STEP * value / max(world, 1)) / 1e9 / peak}
+                "hbm_roofline_frac_whole_step": (ALGO_BYTES_PER_PARTICLE_STEP * value / max(world, 1)) / 1e9 / peak,
+                "host_ms_per_step": host_steps}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()

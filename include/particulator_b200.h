@@ -58,7 +58,7 @@ enum {
     PTL_NPROC_KINDS = 14
 };
 
-#define PTL_MAX_PROCS 32        /* processes per table (reference: tuple length L, collisions.jl:145) */
+#define PTL_MAX_PROCS 128       /* processes per table (reference: tuple length L, collisions.jl:145) */
 #define PTL_PROC_NPAR 6
 
 typedef struct {

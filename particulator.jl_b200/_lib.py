@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PTL_LIB_PATH") or os.path.join(_HERE, "csrc", "libparticulator_b200.so")   # env override: A/B builds of the same CUDA library
 
-MAX_PROCS = 32
+MAX_PROCS = 128
 PROC_NPAR = 6
 MAX_FORCINGS = 4
 MAX_WALLS = 4

@@ -238,6 +238,26 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
             nearb |= fabs(d) < guard;
             if (jsel < 0 && d > 0) jsel = j;
         }
+#ifdef WF_LINEAR_TABLE_SCAN
+    } else if (false) {
+#else
+    } else if (T.mono_mask != 0) {
+#endif
+        // Linear (LXCat) tables: every tabulated rate is >= 0 (checked on the host), so the interpolated running sums are
+        // non-decreasing in j and the first j with cum_j > xi0 is a lower-bound search: ~log2(np) probes of two loads each
+        // instead of np (a real N2/O2 set has 50-80 channels and most sub-steps end in the explicit null row).
+        const double* __restrict__ ca = cum + (size_t)np * pre.i;
+        const double* __restrict__ cb = ca + np;
+        const double w1 = 1 - pre.a;
+#define WF_CUML(j) (pre.a * __ldg(ca + (j)) + w1 * __ldg(cb + (j)))
+        int lo = 0, n = np;
+        while (n > 0) {
+            const int half = n >> 1, mid = lo + half;
+            if (!(WF_CUML(mid) > xi0)) { lo = mid + 1; n -= half + 1; } else n = half;
+        }
+        if (lo < np) { nearb |= fabs(WF_CUML(lo) - xi0) < guard; jsel = lo; }
+        if (lo > 0) nearb |= fabs(WF_CUML(lo - 1) - xi0) < guard;
+#undef WF_CUML
     } else {
         for (int j = 0; j < np; j++) {
             double c0 = __ldg(cum + j + (size_t)np * pre.i), c1 = __ldg(cum + j + (size_t)np * (pre.i + 1));

@@ -587,6 +587,11 @@ EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, doub
         rc = upload_doubles(ctx, cum.data(), cum.size(), &T.d_cum); if (rc) return rc;
         T.v.cum = T.d_cum;
     }
+    {   // binary-search selection needs non-decreasing running sums: every tabulated rate >= 0
+        bool ok = true;
+        for (size_t q = 0; q < (size_t)nprocs * nE && ok; q++) ok = rate[q] >= 0;
+        T.v.mono_mask = ok ? ~0ULL : 0ULL;
+    }
     rc = upload_procs(ctx, T, procs, nprocs); if (rc) return rc;
     T.smem_bytes = sizeof(ptl_process_desc) * nprocs;
     ctx->tables.push_back(T);
@@ -815,9 +820,11 @@ int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
     int32_t rc = read_n(ctx, P, &n); if (rc) return rc;
     if (n == 0) return 0;
     long long ntiles = (n + CMP_TILE - 1) / CMP_TILE;
+    // Scratch is sized by the population's CAPACITY, once: sizing it by the current n re-allocated it almost every step of a
+    // growing avalanche, and a cudaFree/cudaMalloc pair inside droplow! cost up to 200 ms (measured: 2 ms -> 200 ms).
     if ((size_t)ntiles > ctx->tiles_cap) {
         cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets);
-        size_t cap = (size_t)ntiles + 1024;
+        size_t cap = (size_t)((P.v.capacity + CMP_TILE - 1) / CMP_TILE) + 1024;
         CK(cudaMalloc(&ctx->d_tile_counts, sizeof(unsigned int) * cap));
         CK(cudaMalloc(&ctx->d_tile_offsets, sizeof(unsigned long long) * cap));
         ctx->tiles_cap = cap;
@@ -834,7 +841,7 @@ int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
     if (max_moves > 0) {
         if ((size_t)max_moves > ctx->moves_cap) {
             cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
-            size_t cap = (size_t)max_moves + (size_t)max_moves / 4 + 1024;
+            size_t cap = (size_t)(P.v.capacity / 2) + 1024;           // min(actives, dead) <= n / 2 <= capacity / 2
             CK(cudaMalloc(&ctx->d_holes, sizeof(long long) * cap));
             CK(cudaMalloc(&ctx->d_tails, sizeof(long long) * cap));
             ctx->moves_cap = cap;

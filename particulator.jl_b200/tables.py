@@ -240,10 +240,11 @@ def lxcat_table_from_rates(procs, nu, grid_kind, L1, L2):
                           rate=np.ascontiguousarray(rate[perm]), maxrate=maxrate)
 
 
-def synthetic_lxcat_table(n=co.nair, nE=4096, emax_eV=100.0, grid_kind=0):
+def synthetic_lxcat_table(n=co.nair, nE=4096, emax_eV=100.0, grid_kind=0, extra_levels=0):
     """synthetic cross-section set (the reference ships no LXCat data): elastic
     (1e-19 m^2, mass ratio 1.95e-5), three excitations (0.3 / 6.2 / 11 eV), ionisation (15.6 eV) and a
-    dissociative-attachment resonance peaked at 6.5 eV."""
+    dissociative-attachment resonance peaked at 6.5 eV.  `extra_levels` adds that many further excitation
+    channels (thresholds 0.2, 0.45, ... eV): a real N2/O2 set has 50-80 channels."""
     if grid_kind == 0:
         L1, L2 = 0.0, emax_eV * co.eV
         eng = np.linspace(L1, L2, nE)
@@ -263,5 +264,9 @@ def synthetic_lxcat_table(n=co.nair, nE=4096, emax_eV=100.0, grid_kind=0):
            1.5e-22 * np.exp(-0.5 * ((e - 6.5) / 1.0) ** 2)]
     procs = [pr.Elastic(1.95e-5), pr.Excitation(0.3 * co.eV), pr.Excitation(6.2 * co.eV), pr.Excitation(11.0 * co.eV),
              pr.Ionization(15.6 * co.eV), pr.Attachment(0.0)]
+    for k in range(extra_levels):
+        t0 = 0.2 + 0.25 * k
+        sig.append(thr(t0, 2.0e-22, 3.0))
+        procs.append(pr.Excitation(t0 * co.eV))
     nu = np.stack([s * v * n for s in sig])
     return lxcat_table_from_rates(procs, nu, grid_kind, L1, L2)

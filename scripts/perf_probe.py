@@ -6,6 +6,29 @@ import torch
 import particulator_b200 as P
 co = P.co
 
+def main_slow(n, steps, nprocs, dt=1e-12, grid_kind=0):
+    """BASELINE config 5: LXCat-style slow-electron swarm (linear table, explicit null row, null-collision dominated)."""
+    tab = P.synthetic_lxcat_table(grid_kind=grid_kind, extra_levels=max(0, nprocs - 7))   # a real N2/O2 set has 50-80 channels
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = P.Context(device=0, stream=stream)
+    rng = np.random.default_rng(0)
+    st = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * co.eV / co.electron_mass) * 1.2, s=-np.log(1 - rng.random(n)))
+    pop = P.Population(ctx, P.SLOW_ELECTRON, int(1.5 * n), st, tab, 0.0)
+    mp = P.MultiPopulation(("slow", pop))
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -100 * co.Td * co.nair]), None))
+    t = 0.0
+    for it in range(steps):
+        n0 = len(pop)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); t += dt
+        P.advance(mp, psh, t)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1); stt = P.last_advance_stats(mp)
+        P.droplow(pop)
+        print(f"slow n={n0} procs={len(tab.proc)} step {it}: advance {ms:.2f} ms substeps={stt['substeps']} kappa={stt['substeps']/max(stt['rows'],1):.1f} births={stt['births']} "
+              f"-> {n0/ms*1e3:.3e} particle-steps/s, {stt['substeps']/ms*1e3:.3e} substeps/s", flush=True)
+
+
 def main(n=2_000_000, species="electron", steps=3, emin=1e3, emax=1e8, spectrum="exp"):
     comp = P.air_composition(); dt = 2.5e-11
     Fdt = co.elementary_charge * 5e5 * dt
@@ -54,5 +77,9 @@ if __name__ == "__main__":
     ap.add_argument("--n", type=int, default=2_000_000); ap.add_argument("--species", default="electron")
     ap.add_argument("--steps", type=int, default=3); ap.add_argument("--spectrum", default="exp")
     ap.add_argument("--emin", type=float, default=1e3); ap.add_argument("--emax", type=float, default=1e8)
+    ap.add_argument("--lx-procs", type=int, default=7); ap.add_argument("--dt", type=float, default=1e-12)
     a = ap.parse_args()
-    main(a.n, a.species, a.steps, a.emin, a.emax, a.spectrum)
+    if a.species == "slow":
+        main_slow(a.n, a.steps, a.lx_procs, a.dt)
+    else:
+        main(a.n, a.species, a.steps, a.emin, a.emax, a.spectrum)

@@ -303,9 +303,11 @@ def test_capacity_overflow_is_flagged(gctx, air_tables):
     assert gctx.error_flags(clear=True) & 1
 
 
-def test_slow_electron_replay(gctx, octx):
-    """Config 5: LXCat linear table, null-collision dominated, attachment deaths and ionisation births."""
-    tab = P.synthetic_lxcat_table()
+@pytest.mark.parametrize("extra_levels", [0, 57])
+def test_slow_electron_replay(gctx, octx, extra_levels):
+    """Config 5: LXCat linear table, null-collision dominated, attachment deaths and ionisation births.  With 57 extra
+    excitation channels (64 rows, the size of a real N2/O2 set) the kernels select by binary search over the running sums."""
+    tab = P.synthetic_lxcat_table(extra_levels=extra_levels)
     n = 5000
     rng = np.random.default_rng(8)
     st = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * co.eV / co.electron_mass) * 1.2,
