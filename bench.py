@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-shards", type=int, default=int(os.environ.get("PTL_E2E_SHARDS", 12)))
+    ap.add_argument("--e2e-workers", type=int, default=int(os.environ.get("PTL_E2E_WORKERS", 3)))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
@@ -371,7 +373,7 @@ def main():
         # The population is cut into independent shards (particles never interact) that two host threads push through
         # their own library contexts: while one context advances a shard, the other one's H2D / D2H copies run on the
         # copy engines.  Every byte still crosses PCIe inside the timed region.
-        nshards, nworkers = 4, 2
+        nshards, nworkers = max(args.e2e_shards, 1), max(args.e2e_workers, 1)
         bounds = [n_e2e * k // nshards for k in range(nshards + 1)]
         shard_cap = int(1.7 * (bounds[1] - bounds[0])) + 8192
         workers = []

@@ -347,7 +347,9 @@ int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0,
         if (need > ctx->slow_cap) {
             cudaFree(ctx->d_slow_rows);
             ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
-            size_t cap = need + need / 4;
+            // grow geometrically (x2, at least 4 Mi entries): a photon population that grows every step must not pay a
+            // cudaFree/cudaMalloc pair inside most advance! calls (each one synchronises the device)
+            size_t cap = need * 2 > ((size_t)4 << 20) ? need * 2 : ((size_t)4 << 20);
             CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
             ctx->slow_cap = cap;
         }
