@@ -345,7 +345,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_advance_wf<electron> (first pass)",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_advance_bq<electron> (first pass)",
                 "kernel_ms_per_launch": main_ms / max(args.steps, 1), "rows_per_launch": main_rows / max(args.steps, 1),
                 "algorithmic_bytes_per_row": ALGO_BYTES_PER_PARTICLE_STEP,
                 "note": "electrons in STP air do kappa collision sub-steps per particle-step; the kernel is instruction-issue bound, "

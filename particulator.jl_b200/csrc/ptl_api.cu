@@ -117,6 +117,10 @@ bool cuda_ok(ptl_context* ctx, cudaError_t e, const char* what) {
 }
 #define CK(call) do { if (!cuda_ok(ctx, (call), #call)) return PTL_ECUDA; } while (0)
 #define LAUNCHED() do { ctx->launch_total++; CK(cudaGetLastError()); } while (0)
+// Every entry point binds the calling host thread to the context's device: a host thread that was not the one that created
+// the context (the e2e leg of bench.py drives three contexts from three threads) starts on device 0, and on any other rank
+// of a multi-GPU job every launch then failed with PTL_ECUDA.
+#define PTL_BIND(c) do { if (c) cudaSetDevice((c)->device); } while (0)
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -438,6 +442,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
 }
 
 EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -460,6 +465,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
 EXPORT const char* ptl_last_error(ptl_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 EXPORT int32_t ptl_error_flags(ptl_context* ctx, int32_t clear) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     int32_t rc = sync_scalars(ctx);
     if (rc) return rc;
@@ -469,17 +475,20 @@ EXPORT int32_t ptl_error_flags(ptl_context* ctx, int32_t clear) {
 }
 
 EXPORT int32_t ptl_synchronize(ptl_context* ctx) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
 EXPORT int32_t ptl_set_rng(ptl_context* ctx, uint64_t seed, uint32_t step) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     ctx->seed = seed; ctx->step = step;
     return 0;
 }
 EXPORT int32_t ptl_get_rng(ptl_context* ctx, uint64_t* seed, uint32_t* step) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     if (seed) *seed = ctx->seed;
     if (step) *step = ctx->step;
@@ -516,6 +525,7 @@ int32_t upload_procs(ptl_context* ctx, Table& T, const ptl_process_desc* procs, 
 }  // namespace
 
 EXPORT int32_t ptl_sb_table_create(ptl_context* ctx, int32_t ncum, int32_t nE, const double* log_energy, const double* data) {
+    PTL_BIND(ctx);
     if (!ctx || ncum < 2 || nE < 2 || !log_energy || !data) return PTL_EINVAL;
     if (ctx->sbs.size() >= (size_t)MAX_SB) return PTL_ENOMEM;
     Sb s;
@@ -530,6 +540,7 @@ EXPORT int32_t ptl_sb_table_create(ptl_context* ctx, int32_t ncum, int32_t nE, c
 
 EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t nprocs, int32_t k, double xmax, const double* rate,
                                      const double* ratebound, const ptl_process_desc* procs) {
+    PTL_BIND(ctx);
     if (!ctx || order < 1 || order > MAX_ORDER || nprocs < 0 || nprocs > PTL_MAX_PROCS || k < 1 || !(xmax > 0)) return PTL_EINVAL;
     Table T;
     T.v.kind = 0; T.v.order = order; T.v.k = k; T.v.xmax = xmax; T.v.rxmax = 1.0 / xmax;
@@ -575,6 +586,7 @@ EXPORT int32_t ptl_table_create_cheb(ptl_context* ctx, int32_t order, int32_t np
 
 EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, double L1, double L2, int32_t nE, int32_t nprocs,
                                        const double* rate, double maxrate, const ptl_process_desc* procs) {
+    PTL_BIND(ctx);
     if (!ctx || nE < 2 || nprocs < 0 || nprocs > PTL_MAX_PROCS || (grid_kind != 0 && grid_kind != 1)) return PTL_EINVAL;
     Table T;
     T.v.kind = 1; T.v.grid_kind = grid_kind; T.v.L1 = L1; T.v.L2 = L2; T.v.nE = nE; T.v.maxrate = maxrate;
@@ -601,6 +613,7 @@ EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, doub
 }
 
 EXPORT int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, double xmax, const double* ec, const double* pc) {
+    PTL_BIND(ctx);
     if (!ctx || order < 1 || order > MAX_ORDER || k < 1) return PTL_EINVAL;
     if (ctx->cls.size() >= (size_t)MAX_CHEBLOSS) return PTL_ENOMEM;
     ChebLoss c;
@@ -614,6 +627,7 @@ EXPORT int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, 
 }
 
 EXPORT int32_t ptl_table_eval(ptl_context* ctx, int32_t table, int64_t n, const double* energy, double* rates_out, double* bound_out) {
+    PTL_BIND(ctx);
     if (!ctx || table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
     if (n <= 0) return 0;
     const Table& T = ctx->tables[table];
@@ -635,6 +649,7 @@ EXPORT int32_t ptl_table_eval(ptl_context* ctx, int32_t table, int64_t n, const 
 // populations
 // =====================================================================================================
 EXPORT int32_t ptl_population_create(ptl_context* ctx, int32_t species, int64_t capacity, double energy_cut, int32_t table) {
+    PTL_BIND(ctx);
     if (!ctx || species < 0 || species >= PTL_NSPECIES || capacity < 1) return PTL_EINVAL;
     if (table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
     if (ctx->pops.size() >= 64) return PTL_ENOMEM;
@@ -661,6 +676,7 @@ EXPORT int32_t ptl_population_create(ptl_context* ctx, int32_t species, int64_t 
 }
 
 EXPORT int32_t ptl_population_destroy(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -672,6 +688,7 @@ EXPORT int32_t ptl_population_destroy(ptl_context* ctx, int32_t pop) {
 
 EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, const double* x3, const double* p3, const double* w,
                                      const double* t, const double* s, const double* r, const uint8_t* active, const uint64_t* uid) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     if (n < 0 || n > P->v.capacity) return PTL_EINVAL;
@@ -713,6 +730,7 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
 
 EXPORT int64_t ptl_population_download(ptl_context* ctx, int32_t pop, int64_t max_n, double* x3, double* p3, double* w, double* t,
                                        double* s, double* r, uint8_t* active, uint64_t* uid) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     long long n = 0;
@@ -745,6 +763,7 @@ EXPORT int64_t ptl_population_download(ptl_context* ctx, int32_t pop, int64_t ma
 }
 
 EXPORT int64_t ptl_population_n(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     long long n = 0;
@@ -753,17 +772,20 @@ EXPORT int64_t ptl_population_n(ptl_context* ctx, int32_t pop) {
 }
 
 EXPORT int64_t ptl_population_capacity(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     return P ? P->v.capacity : PTL_EHANDLE;
 }
 
 EXPORT int32_t ptl_population_clear(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     return set_n(ctx, *P, 0);
 }
 
 EXPORT int32_t ptl_population_set_n(ptl_context* ctx, int32_t pop, int64_t n) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     if (n < 0 || n > P->v.capacity) return PTL_EINVAL;
@@ -771,6 +793,7 @@ EXPORT int32_t ptl_population_set_n(ptl_context* ctx, int32_t pop, int64_t n) {
 }
 
 EXPORT void* ptl_population_column_ptr(ptl_context* ctx, int32_t pop, int32_t col) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || col < 0 || col >= NCOLS) return nullptr;
     if (col < 10) return P->v.col[col];
@@ -779,6 +802,7 @@ EXPORT void* ptl_population_column_ptr(ptl_context* ctx, int32_t pop, int32_t co
 
 EXPORT int64_t ptl_population_append(ptl_context* ctx, int32_t pop, const double* x3, const double* p3, double w, double t, double s,
                                      double r, uint64_t uid) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !x3 || !p3) return PTL_EHANDLE;
     double p2 = p3[0] * p3[0] + p3[1] * p3[1] + p3[2] * p3[2];
@@ -806,6 +830,7 @@ EXPORT int64_t ptl_population_append(ptl_context* ctx, int32_t pop, const double
 }
 
 EXPORT int32_t ptl_population_deactivate(ptl_context* ctx, int32_t pop, int64_t i) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     long long n = 0;
@@ -860,12 +885,14 @@ int64_t compact(ptl_context* ctx, Pop& P, bool do_flag, double thres) {
 }  // namespace
 
 EXPORT int64_t ptl_droplow(ptl_context* ctx, int32_t pop, double thres) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     return compact(ctx, *P, true, thres);
 }
 
 EXPORT int64_t ptl_repack(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P) return PTL_EHANDLE;
     return compact(ctx, *P, false, 0.0);
@@ -873,6 +900,7 @@ EXPORT int64_t ptl_repack(ptl_context* ctx, int32_t pop) {
 
 // ---- diagnostics -----------------------------------------------------------------------------------------
 EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !out) return PTL_EHANDLE;
     long long n = 0;
@@ -899,6 +927,7 @@ EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
 
 EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, double lo, double hi, int32_t nbins, int32_t logscale,
                              double* out) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !out || nbins < 1 || nbins > 4096 || !(hi > lo)) return PTL_EINVAL;
     long long n = 0;
@@ -918,6 +947,7 @@ EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, do
 }
 
 EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !(p > 0)) return PTL_EINVAL;
     long long n = 0;
@@ -931,6 +961,7 @@ EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
 }
 
 EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
+    PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !(p >= 0)) return PTL_EINVAL;
     long long n = 0;
@@ -948,6 +979,7 @@ EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
 // multi-population + advance
 // =====================================================================================================
 EXPORT int32_t ptl_multipop_create(ptl_context* ctx, const int32_t* pops, int32_t count) {
+    PTL_BIND(ctx);
     if (!ctx || !pops || count < 1 || count > PTL_NSPECIES) return PTL_EINVAL;
     MultiPop m;
     for (int s = 0; s < PTL_NSPECIES; s++) m.by_species[s] = -1;
@@ -963,6 +995,7 @@ EXPORT int32_t ptl_multipop_create(ptl_context* ctx, const int32_t* pops, int32_
 }
 
 EXPORT int32_t ptl_init(ptl_context* ctx, int32_t mp) {
+    PTL_BIND(ctx);
     if (!ctx || mp < 0 || mp >= (int)ctx->mps.size()) return PTL_EHANDLE;
     const MultiPop& M = ctx->mps[mp];
     AdvanceParams A;
@@ -995,6 +1028,7 @@ int32_t ensure_wall(ptl_context* ctx, int k, long long capacity) {
 }  // namespace
 
 EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* pusher, double tfinal, const ptl_callback_desc* cb) {
+    PTL_BIND(ctx);
     if (!ctx || mp < 0 || mp >= (int)ctx->mps.size() || !pusher) return PTL_EHANDLE;
     if (pusher->nforcings < 0 || pusher->nforcings > PTL_MAX_FORCINGS) return PTL_EINVAL;
     const MultiPop& M = ctx->mps[mp];
@@ -1109,6 +1143,7 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
 }
 
 EXPORT int32_t ptl_set_profiling(ptl_context* ctx, int32_t on) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     if (on && !ctx->ev0) {
         CK(cudaEventCreate(&ctx->ev0));
@@ -1119,6 +1154,7 @@ EXPORT int32_t ptl_set_profiling(ptl_context* ctx, int32_t on) {
 }
 
 EXPORT int64_t ptl_launch_count(ptl_context* ctx, int32_t reset) {
+    PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
     long long v = ctx->launch_total;
     if (reset) ctx->launch_total = 0;
@@ -1126,12 +1162,14 @@ EXPORT int64_t ptl_launch_count(ptl_context* ctx, int32_t reset) {
 }
 
 EXPORT int32_t ptl_last_advance_stats(ptl_context* ctx, ptl_advance_stats* out) {
+    PTL_BIND(ctx);
     if (!ctx || !out) return PTL_EINVAL;
     *out = ctx->stats;
     return 0;
 }
 
 EXPORT int32_t ptl_collision_counts(ptl_context* ctx, int32_t table, int64_t* counts, int32_t clear) {
+    PTL_BIND(ctx);
     if (!ctx || table < 0 || table >= (int)ctx->tables.size() || !counts) return PTL_EHANDLE;
     Table& T = ctx->tables[table];
     size_t bytes = sizeof(unsigned long long) * (T.v.nprocs + 1);
@@ -1142,6 +1180,7 @@ EXPORT int32_t ptl_collision_counts(ptl_context* ctx, int32_t table, int64_t* co
 }
 
 EXPORT int64_t ptl_wall_records(ptl_context* ctx, int32_t iwall, int64_t max_n, double* x3, double* p3, double* w, double* t, int32_t clear) {
+    PTL_BIND(ctx);
     if (!ctx || iwall < 0 || iwall >= PTL_MAX_WALLS) return PTL_EINVAL;
     Wall& W = ctx->walls[iwall];
     if (!W.block) return 0;
@@ -1172,6 +1211,7 @@ EXPORT int64_t ptl_wall_records(ptl_context* ctx, int32_t iwall, int64_t max_n, 
 // =====================================================================================================
 EXPORT int32_t ptl_collide_test(ptl_context* ctx, int32_t species, int32_t table, int32_t j, int64_t n, const double* p3, uint64_t uid0,
                                 double* out) {
+    PTL_BIND(ctx);
     if (!ctx || table < 0 || table >= (int)ctx->tables.size()) return PTL_EHANDLE;
     const Table& T = ctx->tables[table];
     if (j < 0 || j >= T.v.nprocs || species < 0 || species >= PTL_NSPECIES || n < 0) return PTL_EINVAL;
@@ -1198,6 +1238,7 @@ __global__ void k_rng_test(unsigned long long uid, uint32_t step, uint32_t seed_
 }  // namespace
 
 EXPORT int32_t ptl_rng_test(ptl_context* ctx, uint64_t uid, uint64_t seed, uint32_t step, int32_t n, double* out) {
+    PTL_BIND(ctx);
     if (!ctx || n < 0 || !out) return PTL_EINVAL;
     if (n == 0) return 0;
     int32_t rc = ensure_tmp(ctx, sizeof(double) * n); if (rc) return rc;
