@@ -368,6 +368,29 @@ def test_lxcat_json_table_replay(gctx, octx, tmp_path):
     assert bad.sum() <= max(2, 0.002 * len(common)), int(bad.sum())
 
 
+def test_context_driven_from_another_host_thread(gctx, air_tables):
+    """One host thread per context is the contract, but not necessarily the thread that created it (bench.py's e2e leg and a
+    Julia task pool both hand contexts to worker threads): every entry point binds the caller to the context's device."""
+    import threading
+    mp, el, ph, po = make_world(gctx, air_tables, 3000, 500, 50, cap=30000, seed=2)
+    res = {}
+
+    def work():
+        try:
+            P.advance(mp, default_pusher(), DT)
+            for q in (el, ph, po):
+                P.droplow(q)
+            res["n"] = len(el)
+            res["p"] = el.download()["p"]
+        except Exception as exc:      # pragma: no cover
+            res["err"] = repr(exc)
+
+    th = threading.Thread(target=work)
+    th.start(); th.join()
+    assert "err" not in res, res.get("err")
+    assert res["n"] > 0 and np.all(np.isfinite(res["p"]))
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at larger sizes (no oracle)
 # ---------------------------------------------------------------------------------------------------
