@@ -34,17 +34,11 @@ constexpr int BQ_SLOTS = BQ_SLOTS_MACRO;            // may be below the chunk ca
 #else
 constexpr int BQ_SLOTS = BQ_THREADS * BQ_CPW;
 #endif
-#ifdef BQ_RING
-// Ring variant: every class list is a circular queue (consumed at the head, appended at the tail), so what a round does not
-// execute simply stays where it is -- no carry-over copies, no second list buffer -- and the pool may hold more slots than a
-// round executes (BQ_SLOTS > 32 * BQ_CHUNKS: the round then finds BQ_CHUNKS full chunks and no warp idles at the barrier).
-constexpr int BQ_RING_SIZE = BQ_SLOTS <= 256 ? 256 : (BQ_SLOTS <= 512 ? 512 : (BQ_SLOTS <= 1024 ? 1024 : 2048));
-static_assert(BQ_SLOTS % 32 == 0 && BQ_SLOTS <= BQ_RING_SIZE, "a class list holds at most every slot once");
-constexpr int BQ_LIST_BYTES = 2 * WS_IDLE * BQ_RING_SIZE;
-#else
 static_assert(BQ_SLOTS <= BQ_THREADS * BQ_CPW && BQ_SLOTS % 32 == 0, "the plan executes at most BQ_CHUNKS full chunks per round");
 constexpr int BQ_LIST_BYTES = 2 * 2 * WS_IDLE * BQ_SLOTS;
-#endif
+// (Measured and dropped: class lists as circular queues -- consumed at the head, appended at the tail, no carry-over copies,
+// pools of 512..608 slots.  14 % slower at 512 slots and it needs rings of twice the pool: a slot that returns to its own
+// class (null collision, rejected RBEB trial) is appended while its old entry is still being read.)
 constexpr int BQ_NCLASS = WS_IDLE;                 // 6 lists
 constexpr int BQ_CHUNKS = BQ_WARPS * BQ_CPW;       // chunks executed per round
 
@@ -72,7 +66,7 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
     S.state = reinterpret_cast<uint32_t*>(ptr); ptr += 4 * BQ_SLOTS;
     S.cnt = nullptr;
     S.order = nullptr;
-    unsigned short* lists = reinterpret_cast<unsigned short*>(ptr); ptr += BQ_LIST_BYTES;   // [2][class][slot], ring: [class][BQ_RING_SIZE]
+    unsigned short* lists = reinterpret_cast<unsigned short*>(ptr); ptr += BQ_LIST_BYTES;   // [2][class][slot]
     unsigned int* cnt = reinterpret_cast<unsigned int*>(ptr);                                               // [3][8]
     double* tsm = reinterpret_cast<double*>(smem_raw + BQ_POOL_BYTES);
 
@@ -103,122 +97,13 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
     // round 0: every slot is an empty LOAD item
-#ifdef BQ_RING
-    for (int q = tid; q < BQ_SLOTS; q += blockDim.x) { lists[WS_LOAD * BQ_RING_SIZE + q] = (unsigned short)q; S.state[q] = WS_LOAD; }
-    if (tid < 24) cnt[tid] = 0;
-#else
     for (int q = tid; q < BQ_SLOTS; q += blockDim.x) { lists[q] = (unsigned short)q; S.state[q] = WS_LOAD; }
     if (tid < 24) cnt[tid] = (tid == WS_LOAD) ? BQ_SLOTS : 0;
-#endif
     const RngCtx rc = {P.step, P.seed_lo, P.seed_hi};
     const double cut = Q.energy_cut;
     unsigned long long nsub = 0;
     __syncthreads();
 
-#ifdef BQ_RING
-    unsigned round = 0;
-    // lane c keeps the head and the tail of class c's queue (every warp holds the same values: the plan is deterministic)
-    unsigned h_c = 0, t_c = (lane == WS_LOAD) ? BQ_SLOTS : 0;
-    constexpr unsigned RMASK = BQ_RING_SIZE - 1;
-    for (;; round++) {
-        const unsigned cb3 = round % 3;
-        unsigned int* acur = cnt + 8 * cb3;                      // appended in this round, per class
-        const unsigned int* aprev = cnt + 8 * ((cb3 + 2) % 3);   // appended in the previous round
-        unsigned int* aold = cnt + 8 * ((cb3 + 1) % 3);          // read in the previous round: clear for the next one
-        if (round > 0 && lane < BQ_NCLASS) t_c += aprev[lane];
-        if (tid < 8) aold[tid] = 0;
-#ifdef BQ_PROFILE
-        const long long pr_t0 = clock64();
-        long long pr_umax = 0;
-#endif
-        // ---- chunk plan, lane c holding class c: full chunks in class order up to the capacity, then the largest remainders ----
-        const int n_c = lane < BQ_NCLASS ? (int)(t_c - h_c) : 0;
-        const int f_c = n_c >> 5, r_c = n_c & 31;
-        int incl = f_c;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        const int start_c = incl - f_c;                          // first plan index of class c's full chunks
-        const int nfull = __shfl_sync(0xffffffffu, incl, BQ_NCLASS - 1);
-        int tot = n_c;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
-        if (__shfl_sync(0xffffffffu, tot, 0) == 0) break;        // block-uniform: every slot retired
-        int rk_c = 0;
-#pragma unroll
-        for (int d = 0; d < BQ_NCLASS; d++) {
-            const int rd = __shfl_sync(0xffffffffu, r_c, d);
-            rk_c += (rd > r_c) || (rd == r_c && d < lane);
-        }
-        const int npartial = nfull < BQ_CHUNKS ? BQ_CHUNKS - nfull : 0;
-        const int ex_c = min(f_c, max(0, BQ_CHUNKS - start_c));  // full chunks of class c that run this round
-        const bool part_c = lane < BQ_NCLASS && r_c > 0 && rk_c < npartial && (r_c >= BQ_PART_MIN || 2 * nfull < BQ_CHUNKS);
-        const unsigned done_c = (unsigned)(ex_c * 32 + (part_c ? r_c : 0));   // consumed from the head of class c's queue
-
-#pragma unroll 1
-        for (int cw = 0; cw < BQ_CPW; cw++) {
-            const int chunk = wid + cw * BQ_WARPS;               // index in the plan order
-            const unsigned mfull = __ballot_sync(0xffffffffu, lane < BQ_NCLASS && chunk >= start_c && chunk < start_c + ex_c);
-            const unsigned mpart = __ballot_sync(0xffffffffu, part_c && rk_c == chunk - nfull);
-            const unsigned msel = mfull ? mfull : mpart;
-            int it = -1;
-            if (msel) {
-                const int my_c = __ffs(msel) - 1;
-                const int k0 = mfull ? (chunk - __shfl_sync(0xffffffffu, start_c, my_c)) : __shfl_sync(0xffffffffu, f_c, my_c);
-                const int nn = __shfl_sync(0xffffffffu, n_c, my_c);
-                const unsigned hh = __shfl_sync(0xffffffffu, h_c, my_c);
-                const int pos = k0 * 32 + lane;
-                if (pos < nn) it = (int)lists[my_c * BQ_RING_SIZE + ((hh + (unsigned)pos) & RMASK)];
-            }
-            const bool has = it >= 0;
-            const unsigned amask = __ballot_sync(0xffffffffu, has);
-#ifdef BQ_PROFILE
-            const long long pr_u0 = clock64();
-#endif
-            int nc = BQ_NCLASS;
-            if (has) {
-                const uint32_t sw = S.state[it];
-                wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, amask, lane, ltmask, row_counter, i0, i1, nsub, rows);
-                __syncwarp(amask);
-                nc = (int)(S.state[it] & 0xffu);                 // next class; IDLE slots are retired
-            }
-            __syncwarp();
-            // append to the tail of the next class's queue: one atomic per destination class and warp
-#pragma unroll
-            for (int c = 0; c < BQ_NCLASS; c++) {
-                const unsigned g = __ballot_sync(0xffffffffu, nc == c);
-                if (g) {                                         // warp-uniform
-                    unsigned base = 0;
-                    if (lane == c) base = t_c + atomicAdd(&acur[c], (unsigned)__popc(g));
-                    base = __shfl_sync(0xffffffffu, base, c);
-                    if (nc == c) lists[c * BQ_RING_SIZE + ((base + (unsigned)__popc(g & ltmask)) & RMASK)] = (unsigned short)it;
-                }
-            }
-#ifdef BQ_PROFILE
-            if (msel) {
-                const long long du = clock64() - pr_u0;
-                pr_umax = du > pr_umax ? du : pr_umax;
-                if (lane == 0) {
-                    const int pc = __ffs(msel) - 1;
-                    atomicAdd(P.dbg + 16 + pc, (unsigned long long)du); atomicAdd(P.dbg + 24 + pc, 1ULL); atomicMax(P.dbg + 32 + pc, (unsigned long long)du);
-                }
-            }
-#endif
-        }
-        h_c += done_c;
-#ifdef BQ_PROFILE
-        const long long pr_b0 = clock64();
-#endif
-        __syncthreads();
-#ifdef BQ_PROFILE
-        if (lane == 0) {
-            const long long pr_t1 = clock64();
-            atomicAdd(P.dbg + 40, (unsigned long long)(pr_t1 - pr_b0)); atomicAdd(P.dbg + 41, 1ULL);
-            atomicAdd(P.dbg + 42, (unsigned long long)(pr_t1 - pr_t0)); atomicAdd(P.dbg + 43, (unsigned long long)pr_umax);
-        }
-#endif
-    }
-
-#else
     unsigned round = 0;
     for (;; round++) {
         const unsigned cb3 = round % 3;
@@ -364,7 +249,6 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
 #endif
     }
 
-#endif
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
     if (lane == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
     if (tid == 0) { atomicMax(P.dbg, (unsigned long long)round); atomicAdd(P.dbg + 1, (unsigned long long)round); atomicAdd(P.dbg + 2, 1ULL); }
