@@ -356,8 +356,9 @@ def main():
     if not args.no_e2e:
         import psutil
         n_now = len(el)
-        if psutil.virtual_memory().available < 3.2 * 89 * n_now:      # host RAM guard: e2e keeps two pinned copies
-            keep = int(psutil.virtual_memory().available / (3.2 * 89))
+        avail = psutil.virtual_memory().available / max(world, 1) * 0.8   # every rank of the box pins its own copies at the same time
+        if avail < 3.2 * 89 * n_now:                                  # host RAM guard: e2e keeps two pinned copies
+            keep = int(avail / (3.2 * 89))
             el.set_n(keep)
             config["e2e_note"] = f"host RAM limited the e2e leg to {keep} of {n_now} electrons"
         d = el.download()
