@@ -14,4 +14,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_ad
 python scripts/kappa_sweep.py > gpurun_out/${TAG}_kappa_sweep.jsonl 2> gpurun_out/${TAG}_kappa.err; cat gpurun_out/${TAG}_kappa_sweep.jsonl | cut -c1-200
 for np in 7 64; do python scripts/perf_probe.py --species slow --n 10000000 --steps 3 --lx-procs $np 2>&1 | tail -1; done | tee gpurun_out/${TAG}_lxcat.log
 python scripts/perf_probe.py --species photon --n 20000000 --steps 3 2>&1 | tail -2 | tee gpurun_out/${TAG}_photon.log
+python scripts/mixed_probe.py --ne 50000000 --ng 50000000 --npos 1000000 --steps 3 2>&1 | tail -1 | tee gpurun_out/${TAG}_mixed.jsonl
 ls -la gpurun_out | tail -20
