@@ -13,11 +13,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 co = P.co
 
 
-def _beam():
-    spec = importlib.util.spec_from_file_location("example_beam", os.path.join(ROOT, "examples", "beam.py"))
+def _load(name):
+    spec = importlib.util.spec_from_file_location("example_" + name, os.path.join(ROOT, "examples", name + ".py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
+
+
+def _beam():
+    return _load("beam")
 
 
 def _summary(r):
@@ -41,3 +45,20 @@ def test_beam_example_gpu_matches_oracle():
     ng, no = _summary(rg), _summary(ro)
     assert abs(ng[0] - no[0]) <= 2 + 0.01 * no[0] and abs(ng[1] - no[1]) <= 2 + 0.02 * no[1]
     assert ng[2] == pytest.approx(no[2], rel=1e-3) and ng[3] == pytest.approx(no[3], rel=1e-3)
+
+
+def test_swarm_example_roulette_keeps_the_weighted_count():
+    """scripts/swarm.jl: roulette! back to ntarget after every outer iteration; the weighted count follows the avalanche."""
+    r = _load("swarm").main(n_init_particles=60, maxp=50000, ntarget=40, iterations=3, tstep=1e-10, ctx=oracle_context())
+    h = r["history"]
+    assert len(h) == 3 and all(n > 40 for _, n, _ in h[:1])
+    assert P.nactives(r["electrons"]) <= 60                       # rouletted
+    assert h[-1][2] >= 0.5 * h[0][1]                              # weighted count is not lost by the roulette (p = ntarget/n, w /= p)
+
+
+@pytest.mark.gpu
+def test_swarm_example_runs_on_gpu():
+    r = _load("swarm").main(n_init_particles=2000, maxp=200000, ntarget=1500, iterations=4, tstep=2e-10, ctx=P.Context(device=0))
+    h = r["history"]
+    assert len(h) == 4 and P.nactives(r["electrons"]) <= 2200
+    assert h[-1][2] > 1500 and np.isfinite(h[-1][2])              # weighted electrons keep growing past the target
