@@ -246,10 +246,10 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
         // Linear (LXCat) tables: every tabulated rate is >= 0 (checked on the host), so the interpolated running sums are
         // non-decreasing in j and the first j with cum_j > xi0 is a lower-bound search: ~log2(np) probes of two loads each
         // instead of np (a real N2/O2 set has 50-80 channels and most sub-steps end in the explicit null row).
-        const double* __restrict__ ca = cum + (size_t)np * pre.i;
-        const double* __restrict__ cb = ca + np;
+        const double2* __restrict__ cp = T.cum2 + (size_t)np * pre.i;     // {row i, row i + 1} pairs: one LDG.128 per probe
         const double w1 = 1 - pre.a;
-#define WF_CUML(j) (pre.a * __ldg(ca + (j)) + w1 * __ldg(cb + (j)))
+        double2 cv_;
+#define WF_CUML(j) (cv_ = __ldg(cp + (j)), pre.a * cv_.x + w1 * cv_.y)
         // (An 8-ary search -- eight independent probes per level, two dependent round trips instead of six for 64 channels --
         // was measured 1.8x SLOWER: 12.7 vs 6.9 ms.  The probes are uncoalesced 8-byte loads, 32 sectors per instruction; the
         // path is bound by that sector traffic, so fewer loads beat shorter chains.)

@@ -37,7 +37,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
 struct Table {
     TableView v{};
     std::vector<ptl_process_desc> procs;
-    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr;
+    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr, *d_cum2 = nullptr;
     ptl_process_desc* d_procs = nullptr;
     unsigned long long* d_counts = nullptr;
     size_t smem_bytes = 0;
@@ -446,7 +446,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     if (!ctx) return PTL_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_cum); cudaFree(t.d_procs); cudaFree(t.d_counts); }
+    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_cum); cudaFree(t.d_cum2); cudaFree(t.d_procs); cudaFree(t.d_counts); }
     for (auto& p : ctx->pops) if (p.block) cudaFree(p.block);
     for (auto& s : ctx->sbs) { cudaFree((void*)s.v.log_energy); cudaFree((void*)s.v.data); }
     for (auto& c : ctx->cls) { cudaFree((void*)c.v.ec); cudaFree((void*)c.v.pc); }
@@ -600,6 +600,17 @@ EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, doub
         }
         rc = upload_doubles(ctx, cum.data(), cum.size(), &T.d_cum); if (rc) return rc;
         T.v.cum = T.d_cum;
+        // the two grid rows a lookup interpolates between, side by side: a search probe is ONE 16-byte load (one sector)
+        // instead of two 8-byte loads from rows np * 8 bytes apart (the LXCat kernel is bound by that sector traffic)
+        std::vector<double> pair((size_t)2 * nprocs * nE);
+        for (int e = 0; e < nE; e++)
+            for (int j = 0; j < nprocs; j++) {
+                size_t q = (size_t)j + (size_t)nprocs * e;
+                pair[2 * q] = cum[q];
+                pair[2 * q + 1] = (e + 1 < nE) ? cum[q + nprocs] : cum[q];
+            }
+        rc = upload_doubles(ctx, pair.data(), pair.size(), &T.d_cum2); if (rc) return rc;
+        T.v.cum2 = reinterpret_cast<const double2*>(T.d_cum2);
     }
     {   // binary-search selection needs non-decreasing running sums: every tabulated rate >= 0
         bool ok = true;

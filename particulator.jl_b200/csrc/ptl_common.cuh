@@ -56,6 +56,7 @@ struct TableView {
     const double* rate;              // cheb: [order, nprocs, k+1]; linear: [nprocs, nE]
     const double* ratebound;         // cheb: [order, k+1]
     const double* cum;               // running sum over processes of `rate` (same layout): selection accelerator
+    const double2* cum2;             // linear tables: {cum[j, e], cum[j, e + 1]} per (j, e): one 16-byte load per search probe
     int grid_kind, nE;
     double L1, L2, maxrate;
     const ptl_process_desc* procs;   // device copy
