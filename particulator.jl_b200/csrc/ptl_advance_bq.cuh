@@ -28,6 +28,9 @@ constexpr int BQ_WARPS = BQ_THREADS / 32;
 #ifndef BQ_PART_MIN
 #define BQ_PART_MIN 28
 #endif
+#ifndef BQ_QUIET_DIV
+#define BQ_QUIET_DIV 2                  // the pool counts as quiet when fewer than 1/BQ_QUIET_DIV of the chunk slots are full chunks
+#endif
 constexpr int BQ_CPW = BQ_CPW_MACRO;               // chunks per warp and round
 #ifdef BQ_SLOTS_MACRO
 constexpr int BQ_SLOTS = BQ_SLOTS_MACRO;            // may be below the chunk capacity (then not every chunk slot is used)
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(BQ_THREADS, BQ_MIN_BLOCKS) k_advance_bq(const 
         // While the pool is busy (at least half of the chunk slots are full chunks) a remainder below BQ_PART_MIN lanes waits
         // and grows instead of costing a whole warp pass for a few lanes (+0.7 %; RBEB/IONFIN chunks ran at 14-17 lanes).
         // With a quiet pool every remainder runs, so nothing can starve at the tail.
-        const bool part_c = lane < BQ_NCLASS && r_c > 0 && rk_c < npartial && (r_c >= BQ_PART_MIN || 2 * nfull < BQ_CHUNKS);
+        const bool part_c = lane < BQ_NCLASS && r_c > 0 && rk_c < npartial && (r_c >= BQ_PART_MIN || BQ_QUIET_DIV * nfull < BQ_CHUNKS);
         const int done_c = f_c * 32 + (part_c ? r_c : 0);        // entries of class c executed this round
 
         // carry-over: what this round does not execute moves to the next round's lists (warp c handles class c)
