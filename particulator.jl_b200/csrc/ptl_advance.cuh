@@ -239,6 +239,8 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
 constexpr int STREAM_THREADS = 256;
 
 template <int SP, bool FIRST>
+// (No minimum-blocks bound on purpose: ptxas picks 118 registers, 2 CTAs per SM, 0.39 ms for 2e7 photons = 87 % of the
+// measured HBM bandwidth.  Forcing 3 or 4 CTAs (80 / 64 registers, spills) measured 0.41 / 0.43 ms; (256, 1) 0.61 ms.)
 __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                                   long long* __restrict__ slow_rows, unsigned long long* slow_count) {
     extern __shared__ double smem[];
