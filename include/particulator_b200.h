@@ -82,8 +82,15 @@ enum {
     PTL_ENODEVICE = -2,   /* no sm_100 device: there is NO CPU fallback */
     PTL_ECUDA = -3,
     PTL_ENOMEM = -4,
-    PTL_EHANDLE = -5
+    PTL_EHANDLE = -5,
+    PTL_ECOMM = -6,       /* NCCL runtime missing or a collective failed (ptl_last_error has the text) */
+    PTL_ECAPACITY = -7    /* ptl_population_append on a full population (@assert population.jl:107); the sticky bit is set too */
 };
+
+/* uid space: uids key the per-particle RNG streams.  Bit 63 clear = sequential uids handed out by the host side
+ * (context counter, ptl_set_uid_counter; rank r of a communicator starts at r * 2^40 + 1); bit 63 set = uids of
+ * particles born in collisions, hashed from (parent uid, parent draw counter). */
+#define PTL_UID_HASHED_BIT 0x8000000000000000ull
 
 /* ---- fields: src/field.jl:4-52 ----------------------------------------------------- */
 enum {
@@ -183,6 +190,14 @@ int32_t ptl_synchronize(ptl_context* ctx);
  * counter = (draw index, advance-call index `step`, seed). */
 int32_t ptl_set_rng(ptl_context* ctx, uint64_t seed, uint32_t step);
 int32_t ptl_get_rng(ptl_context* ctx, uint64_t* seed, uint32_t* step);
+/* Counter behind default uids (uploads / appends without explicit uids).  Restart state: a restored run
+ * must not reissue a live uid.  ptl_population_upload with explicit uids raises it past max(uid). */
+int32_t  ptl_set_uid_counter(ptl_context* ctx, uint64_t next_uid);
+uint64_t ptl_get_uid_counter(ptl_context* ctx);
+/* Tuning knobs outside the reference's surface: "kernel" = lepton advance kernel variant (0 default,
+ * 3 list-scheduled, 4 re-sorting, 5 warp-private pools; all give identical results), "stream" = 0/1
+ * streaming fast path for low-kappa species. */
+int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value);
 
 /* ===================================================================================== */
 /* tables (host-built flat arrays; builders stay on the host, src/collision_table.jl:115-167) */
@@ -243,8 +258,8 @@ int64_t ptl_population_download(ptl_context* ctx, int32_t pop, int64_t max_n,
 int64_t ptl_population_n(ptl_context* ctx, int32_t pop);          /* nparticles   population.jl:78  */
 int64_t ptl_population_capacity(ptl_context* ctx, int32_t pop);
 int32_t ptl_population_clear(ptl_context* ctx, int32_t pop);      /* empty!       population.jl:69  */
-/* add_particle!(popl, state) population.jl:103-113: returns new row index (0-based) or -1
- * if below the energy cut.  Slow path (one particle, host-synchronous). */
+/* add_particle!(popl, state) population.jl:103-113: returns new row index (0-based), -1 if below the
+ * energy cut, PTL_ECAPACITY when the population is full.  Slow path (one particle, host-synchronous). */
 int64_t ptl_population_append(ptl_context* ctx, int32_t pop, const double* x3, const double* p3,
                               double w, double t, double s, double r, uint64_t uid);
 int32_t ptl_population_deactivate(ptl_context* ctx, int32_t pop, int64_t i); /* remove_particle! :120 */
@@ -318,6 +333,41 @@ int32_t ptl_collision_counts(ptl_context* ctx, int32_t table, int64_t* counts, i
  * Returns number of records available; copies up to max_n. */
 int64_t ptl_wall_records(ptl_context* ctx, int32_t iwall, int64_t max_n, double* x3, double* p3,
                          double* w, double* t, int32_t clear);
+
+
+/* ===================================================================================== */
+/* multi-GPU: one context per GPU + a communicator (SURVEY.md section 8b "threading", 8e) */
+/* ===================================================================================== */
+/* The reference is single-process; what replaces it at scale is one process (or host thread) per GPU, each
+ * with its own context and an independent shard of every species.  The advance path needs NO collective.
+ * NCCL (bound at run time: libnccl.so.2 or $PTL_NCCL_LIB) serves the two exchange steps the path has:
+ * reducing what run! prints and the population-control callbacks decide on (src/run.jl:31-40,
+ * src/callback.jl:203,217,239,263), and periodic population rebalancing. */
+#define PTL_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on ONE rank, ship the 128 bytes to the others by any host-side means. */
+int32_t ptl_comm_unique_id(uint8_t* id_out);
+/* ncclCommInitRank on the context's device.  Also moves the context's default-uid counter to
+ * rank * 2^40 + 1 so that uids assigned by different ranks never collide (uids key the RNG streams). */
+int32_t ptl_comm_init(ptl_context* ctx, const uint8_t* id, int32_t rank, int32_t nranks);
+int32_t ptl_comm_destroy(ptl_context* ctx);
+/* Returns 1 when a communicator is attached, 0 otherwise; rank / nranks may be NULL. */
+int32_t ptl_comm_info(ptl_context* ctx, int32_t* rank, int32_t* nranks);
+/* ptl_diag with GLOBAL sums / max over all ranks (identity without a communicator). */
+int32_t ptl_diag_allreduce(ptl_context* ctx, int32_t pop, ptl_diag_out* out);
+/* ptl_histogram summed over all ranks. */
+int32_t ptl_histogram_allreduce(ptl_context* ctx, int32_t pop, int32_t quantity, double lo, double hi,
+                                int32_t nbins, int32_t logscale, double* out);
+/* In-place all-reduce of a small host vector (n <= 4096); op 0 = sum, 1 = max, 2 = min. */
+int32_t ptl_comm_allreduce_f64(ptl_context* ctx, double* inout, int32_t n, int32_t op);
+/* Deterministic rebalancing plan (pure host code, no GPU needed): counts[nranks] ->
+ * moves_out[3*m] = (src, dst, k) "move the last k rows of src to the end of dst".  Nothing moves
+ * while every rank is within `tolerance` (relative) of the mean.  Returns m >= 0. */
+int32_t ptl_rebalance_plan(const int64_t* counts, int32_t nranks, double tolerance,
+                           int64_t* moves_out, int32_t max_moves);
+/* Rebalance one species over the communicator: all-gather of counts, the plan above, ONE grouped
+ * ncclSend/ncclRecv over the 12 column tails (device to device).  Collective: every rank calls it.
+ * Returns the local n afterwards; moved_out (may be NULL) = rows sent (+) or received (-). */
+int64_t ptl_rebalance(ptl_context* ctx, int32_t pop, double tolerance, int64_t* moved_out);
 
 /* ===================================================================================== */
 /* test / diagnostic entry points (deterministic replay of single events)                */

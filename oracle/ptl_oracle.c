@@ -127,8 +127,9 @@ static void child_uids(uint64_t parent, uint32_t idx, uint64_t seed, uint32_t st
     uint32_t ctr[4] = {idx, step, (uint32_t)seed, (uint32_t)(seed >> 32)};
     uint32_t o[4];
     philox4x32_10(ctr, key, o);
-    out[0] = ((uint64_t)o[1] << 32) | o[0];
-    out[1] = ((uint64_t)o[3] << 32) | o[2];
+    /* uid space: bit 63 set = hashed (births), clear = sequential (assigned by the host side); see ptl_set_uid_counter */
+    out[0] = (((uint64_t)o[1] << 32) | o[0]) | PTL_UID_HASHED_BIT;
+    out[1] = (((uint64_t)o[3] << 32) | o[2]) | PTL_UID_HASHED_BIT;
 }
 
 /* nextcoll() = -log(rand())   src/util.jl:17 */
@@ -1168,6 +1169,8 @@ EXPORT int32_t ora_error_flags(ora_context* ctx, int32_t clear) { int32_t f = ct
 EXPORT int32_t ora_synchronize(ora_context* ctx) { (void)ctx; return 0; }
 EXPORT int32_t ora_set_rng(ora_context* ctx, uint64_t seed, uint32_t step) { ctx->seed = seed; ctx->step = step; return 0; }
 EXPORT int32_t ora_get_rng(ora_context* ctx, uint64_t* seed, uint32_t* step) { *seed = ctx->seed; *step = ctx->step; return 0; }
+EXPORT int32_t ora_set_uid_counter(ora_context* ctx, uint64_t next_uid) { if (!ctx || next_uid == 0) return PTL_EINVAL; ctx->next_uid = next_uid; return 0; }
+EXPORT uint64_t ora_get_uid_counter(ora_context* ctx) { return ctx ? ctx->next_uid : 0; }
 
 static double* dupd(const double* src, size_t n) {
     double* d = malloc(sizeof(double) * (n ? n : 1));
@@ -1255,9 +1258,14 @@ EXPORT int32_t ora_population_upload(ora_context* ctx, int32_t pop, int64_t n, c
     memcpy(P->w, w, sizeof(double) * n); memcpy(P->t, t, sizeof(double) * n);
     memcpy(P->s, s, sizeof(double) * n); memcpy(P->r, r, sizeof(double) * n);
     memcpy(P->active, active, n);
-    if (uid) memcpy(P->uid, uid, sizeof(uint64_t) * n);
-    else for (int64_t i = 0; i < n; i++) P->uid[i] = ctx->next_uid + (uint64_t)i;
-    ctx->next_uid += (uint64_t)n;
+    if (uid) {            /* explicit uids: the counter moves past the largest sequential one (restart safety) */
+        memcpy(P->uid, uid, sizeof(uint64_t) * n);
+        for (int64_t i = 0; i < n; i++)
+            if (!(uid[i] & PTL_UID_HASHED_BIT) && uid[i] >= ctx->next_uid) ctx->next_uid = uid[i] + 1;
+    } else {
+        for (int64_t i = 0; i < n; i++) P->uid[i] = ctx->next_uid + (uint64_t)i;
+        ctx->next_uid += (uint64_t)n;
+    }
     P->n = n; P->iup = 0;
     return 0;
 }
@@ -1290,6 +1298,8 @@ EXPORT int64_t ora_population_append(ora_context* ctx, int32_t pop, const double
     for (int c = 0; c < 3; c++) { st.x.v[c] = x3[c]; st.p.v[c] = p3[c]; }
     st.w = w; st.t = t; st.s = s; st.r = r; st.active = 1;
     if (uid == 0) uid = ctx->next_uid++;
+    else if (!(uid & PTL_UID_HASHED_BIT) && uid >= ctx->next_uid) ctx->next_uid = uid + 1;
+    if (P->n >= P->capacity && kinenergy(P->species, st.p) > P->energy_cut) { ctx->flags |= PTL_ERR_CAPACITY_OVERFLOW; return PTL_ECAPACITY; }
     return add_particle(ctx, P, &st, uid);
 }
 

@@ -16,7 +16,7 @@ from .tables import (ChebyshevCollisionTable, CollisionTable, collision_table_fr
                      build_photon_collision_table, synthetic_lxcat_table, lxcat_table_from_rates, loglinrange)
 from . import seltzer
 from .lxcat import load_lxcat, lxcat_collision_table, ensure_elastic
-from ._lib import PtlError, Backend, cuda_backend, LIB_PATH, ABI_SYMBOLS
+from ._lib import PtlError, Backend, cuda_backend, LIB_PATH, ABI_SYMBOLS, ABI_SYMBOLS_CORE
 from .context import Context
 from .field import (ZeroField, HomogeneousField, DoubleLayerField, StepField, ConfinedDoubleLayerField,
                     ElectromagneticField)

@@ -104,10 +104,29 @@ _SIGS = {
     "wall_records": (C.c_int64, [_vp, C.c_int32, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32]),
     "collide_test": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_uint64, _dp]),
     "rng_test": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, _dp]),
+    "set_uid_counter": (C.c_int32, [_vp, C.c_uint64]),
+    "get_uid_counter": (C.c_uint64, [_vp]),
+}
+
+# entry points only the CUDA library has: the multi-GPU communicator (NCCL) and tuning knobs.  The CPU oracle the tests
+# drive through the same host classes is a single-process checker and does not export them.
+_SIGS_DEVICE_ONLY = {
+    "set_option": (C.c_int32, [_vp, C.c_char_p, C.c_int64]),
+    "comm_unique_id": (C.c_int32, [_u8p]),
+    "comm_init": (C.c_int32, [_vp, _u8p, C.c_int32, C.c_int32]),
+    "comm_destroy": (C.c_int32, [_vp]),
+    "comm_info": (C.c_int32, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "diag_allreduce": (C.c_int32, [_vp, C.c_int32, C.POINTER(DiagOut)]),
+    "histogram_allreduce": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp]),
+    "comm_allreduce_f64": (C.c_int32, [_vp, _dp, C.c_int32, C.c_int32]),
+    "rebalance_plan": (C.c_int32, [_i64p, C.c_int32, C.c_double, _i64p, C.c_int32]),
+    "rebalance": (C.c_int64, [_vp, C.c_int32, C.c_double, _i64p]),
 }
 
 #: every symbol include/particulator_b200.h declares (suffix after the prefix)
-ABI_SYMBOLS = sorted(_SIGS)
+ABI_SYMBOLS = sorted(list(_SIGS) + list(_SIGS_DEVICE_ONLY))
+#: the subset both the CUDA library and the test-side CPU oracle export
+ABI_SYMBOLS_CORE = sorted(_SIGS)
 
 
 class PtlError(RuntimeError):
@@ -131,7 +150,9 @@ class Backend:
         self.path, self.prefix = path, prefix
         self.dll = C.CDLL(path)
         self.fn = {}
-        for name, (res, args) in _SIGS.items():
+        sigs = dict(_SIGS)
+        sigs.update({k: v for k, v in _SIGS_DEVICE_ONLY.items() if hasattr(self.dll, prefix + k)})
+        for name, (res, args) in sigs.items():
             f = getattr(self.dll, prefix + name)
             f.restype = res
             if args is not None:

@@ -7,7 +7,7 @@ simulation time, and — because the RNG here is counter-based — the (seed, ad
 k steps + checkpoint + k steps against 2k uninterrupted steps and requires identical state.
 
 File format (one file, little-endian): numpy `.npz` container with
-    meta                 JSON bytes: {"format": "particulator_b200.checkpoint", "version": 1, "t": ..., "seed": ..., "step": ...,
+    meta                 JSON bytes: {"format": "particulator_b200.checkpoint", "version": 1, "t": ..., "seed": ..., "step": ..., "next_uid": ...,
                           "populations": [{"name", "species", "n", "capacity", "energy_cut"}, ...]}
     <name>/x, <name>/p   float64 [n,3], xyz-interleaved like the reference's Vector{SVector{3,Float64}}
     <name>/w,t,s,r       float64 [n];   <name>/active uint8 [n];   <name>/uid uint64 [n]
@@ -30,8 +30,10 @@ def save_checkpoint(path, mpopl, t, extra=None):
     pops = list(mpopl.pairs())
     ctx = pops[0][1].ctx
     seed, step = ctx.get_rng()
+    # next_uid: the counter behind default uids.  Without it a restored run would hand out uids that are still alive
+    # (uids key the RNG streams: two particles with one uid draw the same collision deviates).
     meta = {"format": FORMAT, "version": VERSION, "t": float(t), "seed": int(seed), "step": int(step),
-            "populations": [], "extra": extra or {}}
+            "next_uid": int(ctx.get_uid_counter()), "populations": [], "extra": extra or {}}
     arrays = {}
     for name, popl in pops:
         d = popl.download()
@@ -41,7 +43,11 @@ def save_checkpoint(path, mpopl, t, extra=None):
         for c in _COLUMNS:
             arrays[f"{name}/{c}"] = d[c]
     arrays["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
-    np.savez(path, **arrays)
+    if isinstance(path, (str, bytes)) or hasattr(path, "__fspath__"):
+        with open(path, "wb") as f:          # np.savez(name) would append ".npz" to a name without it
+            np.savez(f, **arrays)
+    else:
+        np.savez(path, **arrays)
     return meta
 
 
@@ -64,6 +70,9 @@ def load_checkpoint(path, mpopl):
     RNG position of the context.  Returns the saved time `t`."""
     meta, state = read_checkpoint(path)
     pops = dict((str(k), v) for k, v in mpopl.pairs())
+    missing = sorted(set(pops) - {p["name"] for p in meta["populations"]})
+    if missing:
+        raise KeyError(f"the MultiPopulation has populations the checkpoint does not hold: {missing}")
     for p in meta["populations"]:
         if p["name"] not in pops:
             raise KeyError(f"checkpoint has population {p['name']!r}, the MultiPopulation does not")
@@ -78,6 +87,8 @@ def load_checkpoint(path, mpopl):
             popl.set_n(0)
     ctx = next(iter(pops.values())).ctx
     ctx.set_rng(meta["seed"], meta["step"])
+    if "next_uid" in meta:
+        ctx.set_uid_counter(max(int(meta["next_uid"]), ctx.get_uid_counter()))
     return meta["t"]
 
 

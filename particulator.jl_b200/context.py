@@ -71,6 +71,16 @@ class Context:
         self.backend.get_rng(self.h, C.byref(s), C.byref(st))
         return s.value, st.value
 
+    def get_uid_counter(self):
+        return int(self.backend.get_uid_counter(self.h))
+
+    def set_uid_counter(self, next_uid):
+        self.check(self.backend.set_uid_counter(self.h, int(next_uid)), "set_uid_counter")
+
+    def set_option(self, name, value):
+        """Tuning knobs outside the reference's surface ("kernel": lepton kernel variant, "stream": streaming fast path)."""
+        self.check(self.backend.set_option(self.h, str(name).encode(), int(value)), "set_option")
+
     # -- tables ---------------------------------------------------------------------------------
     def _proc_descs(self, procs):
         arr = (ProcessDesc * max(1, len(procs)))()

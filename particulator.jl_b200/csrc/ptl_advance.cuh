@@ -26,7 +26,7 @@ struct SmemTable {
 };
 
 // add_particle!(popl, state): population.jl:103-113 + setr! of the newborn (collisions.jl:104,118,128,132)
-__device__ __noinline__ void add_particle(const AdvanceParams& P, int sp, Vec3 x, Vec3 p, double w, double t, double s, uint64_t uid) {
+static __device__ __noinline__ void add_particle(const AdvanceParams& P, int sp, Vec3 x, Vec3 p, double w, double t, double s, uint64_t uid) {
     const PopView& Q = P.pop[sp];
     if (!Q.present) return;
     double eng = kinenergy_rt(sp, p);
@@ -65,7 +65,7 @@ __device__ __forceinline__ double own_ratebound(const AdvanceParams& P, const Sm
 
 // setr!: collisions.jl:63-74
 template <int SP>
-__device__ __noinline__ double setr(const AdvanceParams& P, const SmemTable& S, Vec3 p) {
+static __device__ __noinline__ double setr(const AdvanceParams& P, const SmemTable& S, Vec3 p) {
     double eng = kinenergy<SP>(p);
     if (eng < P.pop[SP].energy_cut) return 0.0;
     return own_ratebound<SP>(P, S, eng);
@@ -344,7 +344,7 @@ __global__ void k_init_r(const __grid_constant__ AdvanceParams P, long long n) {
 }
 
 // bit-exact tier entry point: presample + rate(j) + ratebound for n energies
-__global__ void k_table_eval(TableView T, long long n, const double* __restrict__ energy, double* __restrict__ rates,
+static __global__ void k_table_eval(TableView T, long long n, const double* __restrict__ energy, double* __restrict__ rates,
                              double* __restrict__ bound, int* flags) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void wf_put3(const WfPool& S, int c0, int it, Vec3 v)
 // and takes at most ~256 sub-steps per call so that the unit stays as short as the others in its round; the slot keeps
 // the WF_COAST flag until no further repeated sub-step fits or the next one would reach the cut.
 template <int SP>
-__device__ __noinline__ unsigned long long wf_coast_below_cut(const AdvanceParams& P, const WfPool& S, int it, double cut) {
+static __device__ __noinline__ unsigned long long wf_coast_below_cut(const AdvanceParams& P, const WfPool& S, int it, double cut) {
     Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
     double t = WFD(WD_T, it), trem = WFD(WD_TREM, it);
     const double tnext = WFD(WD_S, it) * frcp(WFD(WD_R, it));       // same expression as the STEP unit (:67)
@@ -151,7 +151,7 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
 
 // cold paths of the selection (tables that do not fit the fast layout; exact sequential scan inside the guard band)
 template <int TK>
-__device__ __noinline__ int wf_select_generic(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, Pre pre,
+static __device__ __noinline__ int wf_select_generic(const AdvanceParams& P, const TableView& T, const double* __restrict__ cum, Pre pre,
                                               double xi0, double r, int* rbv) {
     bool b;
     int j = wf_select<TK, false>(P, T, cum, pre, xi0, r, b);
@@ -159,7 +159,7 @@ __device__ __noinline__ int wf_select_generic(const AdvanceParams& P, const Tabl
     return j;
 }
 template <int TK>
-__device__ __noinline__ int wf_select_sequential(const TableView& T, Pre pre, double xi0, int* rbv) {
+static __device__ __noinline__ int wf_select_sequential(const TableView& T, Pre pre, double xi0, int* rbv) {
     const int np = T.nprocs;
     double xi = xi0;
     int jsel = -1;

@@ -2,386 +2,17 @@
 // upload, and the host-side launch logic of every kernel (advance pass loop, compaction, diagnostics).
 // Plain C signatures only; no torch / C++ types cross the boundary.  There is NO CPU fallback: a
 // context can only be created on a compute-capability-10.x device.
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-#include <chrono>
-
+#include "ptl_host.h"
 #include "ptl_advance.cuh"
-#include "ptl_advance_wf.cuh"
-#ifdef PTL_WITH_AQ
-#include "ptl_advance_aq.cuh"   // queue-driven experiment (autonomous warps); not faster than the list-scheduled kernel
-#endif
-#include "ptl_advance_bq.cuh"
 #include "ptl_store.cuh"
 
 using namespace ptl;
+using namespace ptl_host;
+static_assert(ptl::DIAG_NVAL == ptl::DIAG_NVAL_HOST, "diagnostic vector length");
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
 namespace {
-
-struct DeviceScalars {            // one small device block mirrored in pinned host memory
-    int flags;
-    int _pad;
-    unsigned long long substeps[PTL_NSPECIES], births, tile_counter, total, nmoves, slow_count;
-    unsigned long long pop_n[64];
-    unsigned long long wall_n[PTL_MAX_WALLS];
-    double diag[DIAG_NVAL];
-    unsigned long long dbg[64];    // PTL_TRACE: max / sum of scheduler rounds per CTA, CTA count
-};
-
-struct Table {
-    TableView v{};
-    std::vector<ptl_process_desc> procs;
-    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr, *d_cum2 = nullptr;
-    ptl_process_desc* d_procs = nullptr;
-    unsigned long long* d_counts = nullptr;
-    size_t smem_bytes = 0;
-};
-
-struct Pop {
-    PopView v{};
-    void* block = nullptr;
-    long long iup = 0;
-    int table = -1;
-    int slot = -1;                // index into DeviceScalars.pop_n
-    double kappa_est = -1;        // measured sub-steps per row in the last advance (< 0: unknown)
-    long long rows_last = 0;
-    bool alive = false;
-};
-
-struct MultiPop {
-    std::vector<int> pops;
-    int by_species[PTL_NSPECIES];
-};
-
-struct Sb { SbView v{}; };
-struct ChebLoss { ChebLossView v{}; };
-
-struct Wall {
-    WallBuf b{};
-    void* block = nullptr;
-};
-
-}  // namespace
-
-struct ptl_context {
-    int device = 0;
-    int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    std::vector<Table> tables;
-    std::vector<Pop> pops;
-    std::vector<Sb> sbs;
-    std::vector<ChebLoss> cls;
-    std::vector<MultiPop> mps;
-    Wall walls[PTL_MAX_WALLS];
-    DeviceScalars* d_sc = nullptr;
-    DeviceScalars* h_sc = nullptr;     // pinned
-    uint64_t seed = 0;
-    uint32_t step = 0;
-    uint64_t next_uid = 1;
-    ptl_advance_stats stats{};
-    std::string err;
-    // scratch
-    void* stage[2] = {nullptr, nullptr};
-    size_t stage_rows = 0;
-    unsigned int* d_tile_counts = nullptr;
-    unsigned long long* d_tile_offsets = nullptr;
-    size_t tiles_cap = 0;
-    long long *d_holes = nullptr, *d_tails = nullptr;
-    size_t moves_cap = 0;
-    double* d_partial = nullptr;
-    int partial_blocks = 0;
-    void* d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    long long* d_slow_rows = nullptr;  // rows the streaming photon kernel deferred to the general kernel
-    size_t slow_cap = 0;
-    int kernel_mode = 0;               // PTL_KERNEL: wf / aq = alternative lepton kernels, nostream = no streaming fast path (A/B measurements)
-    long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
-    bool profiling = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool ev_pending = false;
-};
-
-namespace {
-
-bool cuda_ok(ptl_context* ctx, cudaError_t e, const char* what) {
-    if (e == cudaSuccess) return true;
-    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
-    return false;
-}
-#define CK(call) do { if (!cuda_ok(ctx, (call), #call)) return PTL_ECUDA; } while (0)
-#define LAUNCHED() do { ctx->launch_total++; CK(cudaGetLastError()); } while (0)
-// Every entry point binds the calling host thread to the context's device: a host thread that was not the one that created
-// the context (the e2e leg of bench.py drives three contexts from three threads) starts on device 0, and on any other rank
-// of a multi-GPU job every launch then failed with PTL_ECUDA.
-#define PTL_BIND(c) do { if (c) cudaSetDevice((c)->device); } while (0)
-
-size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
-
-int32_t sync_scalars(ptl_context* ctx) {
-    CK(cudaMemcpyAsync(ctx->h_sc, ctx->d_sc, sizeof(DeviceScalars), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return 0;
-}
-
-Pop* get_pop(ptl_context* ctx, int32_t pop) {
-    if (!ctx || pop < 0 || pop >= (int)ctx->pops.size() || !ctx->pops[pop].alive) return nullptr;
-    return &ctx->pops[pop];
-}
-
-unsigned long long* dev_n(ptl_context* ctx, const Pop& P) { return &ctx->d_sc->pop_n[P.slot]; }
-
-// read popl.n from the device (clamped to capacity; overflow raises the sticky flag)
-int32_t read_n(ptl_context* ctx, Pop& P, long long* out) {
-    int32_t rc = sync_scalars(ctx);
-    if (rc) return rc;
-    long long n = (long long)ctx->h_sc->pop_n[P.slot];
-    if (n > P.v.capacity) {
-        n = P.v.capacity;
-        unsigned long long nn = (unsigned long long)n;
-        CK(cudaMemcpyAsync(dev_n(ctx, P), &nn, sizeof(nn), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    *out = n;
-    return 0;
-}
-
-int32_t set_n(ptl_context* ctx, Pop& P, long long n) {
-    unsigned long long nn = (unsigned long long)n;
-    ctx->h_sc->pop_n[P.slot] = nn;
-    CK(cudaMemcpyAsync(dev_n(ctx, P), &ctx->h_sc->pop_n[P.slot], sizeof(nn), cudaMemcpyHostToDevice, ctx->stream));
-    return 0;
-}
-
-int32_t ensure_stage(ptl_context* ctx) {
-    const size_t rows = (size_t)1 << 22;   // 4 Mi rows x 24 B = 96 MiB per staging buffer
-    if (ctx->stage_rows >= rows) return 0;
-    for (int b = 0; b < 2; b++) CK(cudaMalloc(&ctx->stage[b], rows * 3 * sizeof(double)));
-    ctx->stage_rows = rows;
-    return 0;
-}
-
-int32_t ensure_tmp(ptl_context* ctx, size_t bytes) {
-    if (ctx->tmp_bytes >= bytes) return 0;
-    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
-    ctx->d_tmp = nullptr; ctx->tmp_bytes = 0;
-    CK(cudaMalloc(&ctx->d_tmp, bytes));
-    ctx->tmp_bytes = bytes;
-    return 0;
-}
-
-void fill_params(ptl_context* ctx, const MultiPop* mp, AdvanceParams& A) {
-    memset(&A, 0, sizeof(A));
-    for (int s = 0; s < PTL_NSPECIES; s++) {
-        int pi = mp ? mp->by_species[s] : -1;
-        if (pi >= 0) {
-            A.pop[s] = ctx->pops[pi].v;
-            A.pop[s].present = 1;
-            A.tab[s] = ctx->tables[ctx->pops[pi].table].v;
-        }
-    }
-    for (size_t i = 0; i < ctx->sbs.size() && i < (size_t)MAX_SB; i++) A.sb[i] = ctx->sbs[i].v;
-    for (size_t i = 0; i < ctx->cls.size() && i < (size_t)MAX_CHEBLOSS; i++) A.cl[i] = ctx->cls[i].v;
-    for (int k = 0; k < PTL_MAX_WALLS; k++) A.wall[k] = ctx->walls[k].b;
-    A.seed_lo = (uint32_t)ctx->seed;
-    A.seed_hi = (uint32_t)(ctx->seed >> 32);
-    A.step = ctx->step;
-    A.flags = &ctx->d_sc->flags;
-    A.substeps = ctx->d_sc->substeps;
-    A.births = &ctx->d_sc->births;
-    A.dbg = ctx->d_sc->dbg;
-}
-
-template <int SP, bool FIRST, bool CB>
-int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t smem, const long long* rows = nullptr) {
-    auto kern = k_advance<SP, FIRST, CB>;
-    static bool configured = false;
-    static int blocks_per_sm = 1;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        configured = true;
-    }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, ADV_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
-        blocks_per_sm = 1;
-    long long tiles = (i1 - i0 + 31) / 32;
-    long long want = (tiles + (ADV_THREADS / 32) - 1) / (ADV_THREADS / 32);
-    long long grid = (long long)ctx->sm_count * blocks_per_sm;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
-    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-    LAUNCHED();
-    ctx->stats.launches++;
-    return 0;
-}
-
-// wavefront variant (collision-dominated species): persistent CTAs, shared-memory particle pool
-template <int SP, int TK, bool FIRST, bool CB>
-int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows) {
-    auto kern = k_advance_wf<SP, TK, FIRST, CB>;
-    const TableView& TV = A.tab[SP];
-    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
-    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
-    (void)table_smem;
-    size_t smem = wf_pool_bytes() + tsm + 32;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        configured = true;
-    }
-    int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WF_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
-        blocks_per_sm = 1;
-    long long nrow = i1 - i0;
-    long long want = (nrow + WF_THREADS - 1) / WF_THREADS;
-    long long grid = (long long)ctx->sm_count * blocks_per_sm;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
-    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-    LAUNCHED();
-    ctx->stats.launches++;
-    return 0;
-}
-
-#ifdef PTL_WITH_AQ
-// queue-driven variant: autonomous warps, per-class ring buffers in shared memory
-template <int SP, int TK, bool FIRST, bool CB>
-int32_t launch_advance_aq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1) {
-    auto kern = k_advance_aq<SP, TK, FIRST, CB>;
-    const TableView& TV = A.tab[SP];
-    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
-    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
-    size_t smem = AQ_POOL_BYTES + tsm + 32;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        configured = true;
-    }
-    int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, AQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
-        blocks_per_sm = 1;
-    long long rows = i1 - i0;
-    long long want = (rows + AQ_SLOTS - 1) / AQ_SLOTS;
-    long long grid = (long long)ctx->sm_count * blocks_per_sm;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
-    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, AQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-    LAUNCHED();
-    ctx->stats.launches++;
-    return 0;
-}
-
-#endif
-
-// list-scheduled variant (incremental per-class lists, one barrier per round, two chunks per warp)
-template <int SP, int TK, bool FIRST, bool CB>
-int32_t launch_advance_bq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, const long long* rows) {
-    auto kern = k_advance_bq<SP, TK, FIRST, CB>;
-    const TableView& TV = A.tab[SP];
-    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
-    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
-    size_t smem = BQ_POOL_BYTES + tsm + 32;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-        configured = true;
-    }
-    int blocks_per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, BQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
-        blocks_per_sm = 1;
-    long long nrow = i1 - i0;
-    long long want = (nrow + BQ_SLOTS - 1) / BQ_SLOTS;
-    long long grid = (long long)ctx->sm_count * blocks_per_sm;
-    if (grid > want) grid = want;
-    if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
-    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, BQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-    LAUNCHED();
-    ctx->stats.launches++;
-    return 0;
-}
-
-template <int SP, bool FIRST, bool CB>
-int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows = nullptr) {
-    // default: list-scheduled kernel (k_advance_bq).  PTL_KERNEL=wf selects the re-sorting kernel, PTL_KERNEL=aq the
-    // queue-driven one (only when compiled with -DPTL_WITH_AQ) — kept for A/B measurements.
-#ifdef PTL_WITH_AQ
-    if (ctx->kernel_mode == 1 && rows == nullptr) {
-        if (A.tab[SP].kind == 0) return launch_advance_aq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1);
-        return launch_advance_aq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1);
-    }
-#endif
-    if (ctx->kernel_mode != 4) {
-        if (A.tab[SP].kind == 0) return launch_advance_bq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, rows);
-        return launch_advance_bq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, rows);
-    }
-    if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
-    return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
-}
-
-// First-pass kernel choice.  Photons, and any species whose measured kappa (sub-steps per row of the previous advance)
-// is small, are HBM-bound: free flights go through the streaming kernel and only the rows that collide within dt are
-// deferred, through an index list, to the general kernel of the species (one particle per lane for photons, wavefront
-// for leptons).  Collision-dominated populations go straight to the wavefront kernel.
-template <int SP>
-int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem, bool low_kappa) {
-    const long long* rows = nullptr;
-    if ((SP == PTL_PHOTON || low_kappa) && !cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->kernel_mode != 2) {
-        size_t need = (size_t)(i1 - i0);
-        if (need > ctx->slow_cap) {
-            cudaFree(ctx->d_slow_rows);
-            ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
-            // grow geometrically (x2, at least 4 Mi entries): a photon population that grows every step must not pay a
-            // cudaFree/cudaMalloc pair inside most advance! calls (each one synchronises the device)
-            size_t cap = need * 2 > ((size_t)4 << 20) ? need * 2 : ((size_t)4 << 20);
-            CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
-            ctx->slow_cap = cap;
-        }
-        CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
-        const TableView& TV = A.tab[SP];
-        size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
-        long long pairs = (i1 - i0 + 1) / 2;
-        long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
-        long long maxgrid = (long long)ctx->sm_count * 8;
-        if (grid > maxgrid) grid = maxgrid;
-        bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-        if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-        else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-        if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
-        LAUNCHED();
-        ctx->stats.launches++;
-        rows = ctx->d_slow_rows;
-        cb = false;
-    }
-    if constexpr (SP == PTL_PHOTON) {
-        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
-        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
-    } else {
-        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
-        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
-    }
-}
 
 int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem, bool low_kappa) {
     switch (species) {
@@ -403,6 +34,14 @@ int32_t launch_advance(ptl_context* ctx, int species, const AdvanceParams& A, lo
 
 unsigned grid_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// fold the device-side maximum of the explicitly uploaded sequential uids into the host counter
+int32_t refresh_next_uid(ptl_context* ctx) {
+    int32_t rc = sync_scalars(ctx);
+    if (rc) return rc;
+    if (ctx->h_sc->max_uid >= ctx->next_uid) ctx->next_uid = ctx->h_sc->max_uid + 1;
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -421,7 +60,10 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     ptl_context* ctx = new ptl_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (const char* km = getenv("PTL_KERNEL")) ctx->kernel_mode = !strcmp(km, "aq") ? 1 : (!strcmp(km, "nostream") ? 2 : (!strcmp(km, "wf") ? 4 : 0));
+    if (const char* km = getenv("PTL_KERNEL")) {      // A/B measurements; ptl_set_option does the same per context
+        ctx->lepton_kernel = !strcmp(km, "wq") ? 5 : (!strcmp(km, "bq") ? 3 : (!strcmp(km, "wf") ? 4 : 0));
+        if (!strcmp(km, "nostream")) ctx->use_stream = false;
+    }
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -453,7 +95,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     for (auto& w : ctx->walls) if (w.block) cudaFree(w.block);
     for (int b = 0; b < 2; b++) if (ctx->stage[b]) cudaFree(ctx->stage[b]);
     cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets); cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
-    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp); cudaFree(ctx->d_slow_rows);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp); cudaFree(ctx->d_slow_rows); cudaFree(ctx->d_coll);
     cudaFree(ctx->d_sc);
     cudaFreeHost(ctx->h_sc);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
@@ -487,6 +129,34 @@ EXPORT int32_t ptl_set_rng(ptl_context* ctx, uint64_t seed, uint32_t step) {
     ctx->seed = seed; ctx->step = step;
     return 0;
 }
+// Tuning / A-B knobs that are not part of the reference's surface.  "kernel": lepton advance kernel variant
+// (0 = default, 3 = bq list-scheduled, 4 = wf re-sorting, 5 = wq warp-private); "stream": 0 disables the streaming fast path.
+EXPORT int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value) {
+    PTL_BIND(ctx);
+    if (!ctx || !name) return PTL_EINVAL;
+    if (!strcmp(name, "kernel")) {
+        if (value != 0 && value != 3 && value != 4 && value != 5) return PTL_EINVAL;
+        ctx->lepton_kernel = (int)value;
+        return 0;
+    }
+    if (!strcmp(name, "stream")) { ctx->use_stream = value != 0; return 0; }
+    ctx->err = std::string("unknown option ") + name;
+    return PTL_EINVAL;
+}
+
+// uid counter behind default uids (ptl_population_upload / ptl_population_append without explicit uids).  Part of the
+// restart state: a restored run must not reissue a uid that is still alive, because uids key the RNG streams.
+EXPORT int32_t ptl_set_uid_counter(ptl_context* ctx, uint64_t next_uid) {
+    if (!ctx || next_uid == 0) return PTL_EINVAL;
+    ctx->next_uid = next_uid;
+    return 0;
+}
+EXPORT uint64_t ptl_get_uid_counter(ptl_context* ctx) {
+    PTL_BIND(ctx);
+    if (!ctx || refresh_next_uid(ctx)) return 0;
+    return ctx->next_uid;
+}
+
 EXPORT int32_t ptl_get_rng(ptl_context* ctx, uint64_t* seed, uint32_t* step) {
     PTL_BIND(ctx);
     if (!ctx) return PTL_EINVAL;
@@ -725,14 +395,19 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
         CK(cudaMemcpyAsync(P->v.col[COL_S], s, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->v.col[COL_R], r, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->v.active, active, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-        if (uid) {
+        if (uid) {   // explicit uids: the default-uid counter must end up past the largest sequential one (folded in lazily)
             CK(cudaMemcpyAsync(P->v.uid, uid, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+            int blocks = (int)((n + 1023) / 1024);
+            if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+            k_uid_max<<<blocks, 256, 0, ctx->stream>>>(P->v.uid, n, &ctx->d_sc->max_uid);
+            LAUNCHED();
         } else {
+            rc = refresh_next_uid(ctx); if (rc) return rc;
             k_fill_uid<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.uid, ctx->next_uid, n);
             LAUNCHED();
+            ctx->next_uid += (uint64_t)n;
         }
     }
-    ctx->next_uid += (uint64_t)n;
     P->iup = 0;
     rc = set_n(ctx, *P, n); if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));   // host arrays are only borrowed for the duration of the call
@@ -823,16 +498,21 @@ EXPORT int64_t ptl_population_append(ptl_context* ctx, int32_t pop, const double
     if (eng <= P->v.energy_cut) return -1;   // population.jl:105
     long long n = 0;
     int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
-    if (n >= P->v.capacity) {
-        ctx->h_sc->flags |= PTL_ERR_CAPACITY_OVERFLOW;
-        int f = PTL_ERR_CAPACITY_OVERFLOW;
-        cudaMemcpyAsync(&ctx->d_sc->flags, &f, sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-        return -1;
+    if (n >= P->v.capacity) {      // @assert n < length(particles)  population.jl:107: sticky bit (OR-ed, other bits survive) + its own code
+        k_or_flags<<<1, 1, 0, ctx->stream>>>(&ctx->d_sc->flags, PTL_ERR_CAPACITY_OVERFLOW);
+        LAUNCHED();
+        ctx->err = "ptl_population_append: population is full";
+        return PTL_ECAPACITY;
     }
     double vals[10] = {x3[0], x3[1], x3[2], p3[0], p3[1], p3[2], w, t, s, r};
     for (int c = 0; c < 10; c++) CK(cudaMemcpyAsync(P->v.col[c] + n, &vals[c], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     uint8_t one = 1;
-    if (uid == 0) uid = ctx->next_uid++;
+    if (uid == 0) {
+        rc = refresh_next_uid(ctx); if (rc) return rc;
+        uid = ctx->next_uid++;
+    } else if (!(uid & PTL_UID_HASHED_BIT) && uid >= ctx->next_uid) {
+        ctx->next_uid = uid + 1;
+    }
     CK(cudaMemcpyAsync(P->v.active + n, &one, 1, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(P->v.uid + n, &uid, sizeof(uid), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -909,6 +589,51 @@ EXPORT int64_t ptl_repack(ptl_context* ctx, int32_t pop) {
     return compact(ctx, *P, false, 0.0);
 }
 
+namespace ptl_host {
+int32_t diag_local_launch(ptl_context* ctx, Pop& P, long long n) {
+    if (n > 0) {
+        int blocks = (int)((n + DIAG_THREADS - 1) / DIAG_THREADS);
+        if (blocks > ctx->partial_blocks) blocks = ctx->partial_blocks;
+        DISPATCH_SPECIES(P.v.species, k_diag_partial<SP><<<blocks, DIAG_THREADS, 0, ctx->stream>>>(P.v, n, ctx->d_partial));
+        LAUNCHED();
+        k_diag_final<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, blocks, ctx->d_sc->diag);
+        LAUNCHED();
+    } else {
+        for (int q = 0; q < DIAG_NVAL; q++) ctx->h_sc->diag[q] = 0;
+        ctx->h_sc->diag[10] = -INFINITY;
+        CK(cudaMemcpyAsync(ctx->d_sc->diag, ctx->h_sc->diag, sizeof(double) * DIAG_NVAL, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->h_sc->diag[11] = (double)n;
+    CK(cudaMemcpyAsync(ctx->d_sc->diag + 11, ctx->h_sc->diag + 11, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+void diag_unpack(const double* d, ptl_diag_out* out) {
+    memset(out, 0, sizeof(*out));
+    out->nactive = (int64_t)llround(d[0]);
+    out->weight = d[1]; out->wenergy = d[2];
+    for (int c = 0; c < 3; c++) { out->wx[c] = d[3 + c]; out->wx2[c] = d[6 + c]; }
+    out->wr2 = d[9];
+    out->maxenergy = d[10];
+    out->n = (int64_t)llround(d[11]);
+}
+
+int32_t histogram_local_launch(ptl_context* ctx, Pop& P, int32_t quantity, double lo, double hi, int32_t nbins, int32_t logscale) {
+    long long n = 0;
+    int32_t rc = read_n(ctx, P, &n); if (rc) return rc;
+    rc = ensure_tmp(ctx, sizeof(double) * nbins); if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_tmp, 0, sizeof(double) * nbins, ctx->stream));
+    if (n > 0) {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+        DISPATCH_SPECIES(P.v.species, k_histogram<SP><<<blocks, 256, sizeof(double) * nbins, ctx->stream>>>(P.v, n, quantity, lo, hi, nbins, logscale,
+                                                                                                            (double*)ctx->d_tmp));
+        LAUNCHED();
+    }
+    return 0;
+}
+}  // namespace ptl_host
+
 // ---- diagnostics -----------------------------------------------------------------------------------------
 EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
     PTL_BIND(ctx);
@@ -916,23 +641,9 @@ EXPORT int32_t ptl_diag(ptl_context* ctx, int32_t pop, ptl_diag_out* out) {
     if (!P || !out) return PTL_EHANDLE;
     long long n = 0;
     int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
-    memset(out, 0, sizeof(*out));
-    out->n = n;
-    out->maxenergy = -INFINITY;
-    if (n == 0) return 0;
-    int blocks = (int)((n + DIAG_THREADS - 1) / DIAG_THREADS);
-    if (blocks > ctx->partial_blocks) blocks = ctx->partial_blocks;
-    DISPATCH_SPECIES(P->v.species, k_diag_partial<SP><<<blocks, DIAG_THREADS, 0, ctx->stream>>>(P->v, n, ctx->d_partial));
-    LAUNCHED();
-    k_diag_final<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, blocks, ctx->d_sc->diag);
-    LAUNCHED();
+    rc = diag_local_launch(ctx, *P, n); if (rc) return rc;
     rc = sync_scalars(ctx); if (rc) return rc;
-    const double* d = ctx->h_sc->diag;
-    out->nactive = (int64_t)llround(d[0]);
-    out->weight = d[1]; out->wenergy = d[2];
-    for (int c = 0; c < 3; c++) { out->wx[c] = d[3 + c]; out->wx2[c] = d[6 + c]; }
-    out->wr2 = d[9];
-    out->maxenergy = d[10];
+    diag_unpack(ctx->h_sc->diag, out);
     return 0;
 }
 
@@ -941,17 +652,7 @@ EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, do
     PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
     if (!P || !out || nbins < 1 || nbins > 4096 || !(hi > lo)) return PTL_EINVAL;
-    long long n = 0;
-    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
-    rc = ensure_tmp(ctx, sizeof(double) * nbins); if (rc) return rc;
-    CK(cudaMemsetAsync(ctx->d_tmp, 0, sizeof(double) * nbins, ctx->stream));
-    if (n > 0) {
-        int blocks = (int)((n + 255) / 256);
-        if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
-        DISPATCH_SPECIES(P->v.species, k_histogram<SP><<<blocks, 256, sizeof(double) * nbins, ctx->stream>>>(P->v, n, quantity, lo, hi, nbins, logscale,
-                                                                                                             (double*)ctx->d_tmp));
-        LAUNCHED();
-    }
+    int32_t rc = histogram_local_launch(ctx, *P, quantity, lo, hi, nbins, logscale); if (rc) return rc;
     CK(cudaMemcpyAsync(out, ctx->d_tmp, sizeof(double) * nbins, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1045,6 +746,28 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
     const MultiPop& M = ctx->mps[mp];
     bool has_cb = cb && (cb->nwalls > 0 || cb->count_collisions);
     if (cb && (cb->nwalls < 0 || cb->nwalls > PTL_MAX_WALLS)) return PTL_EINVAL;
+    // descriptors come from a foreign caller: everything the kernels index with is range-checked here
+    if (pusher->kind != PTL_PUSHER_NULL && pusher->kind != PTL_PUSHER_RK2) { ctx->err = "unknown pusher kind"; return PTL_EINVAL; }
+    for (int k = 0; k < pusher->nforcings; k++) {
+        const ptl_forcing_desc& f = pusher->forcing[k];
+        if (f.kind < PTL_FORCE_NONE || f.kind > PTL_FORCE_CHEB_CONTINUUM) { ctx->err = "unknown forcing kind"; return PTL_EINVAL; }
+        if (f.kind == PTL_FORCE_EM && (f.e.kind < PTL_FIELD_ZERO || f.e.kind > PTL_FIELD_CONFINED_DL || f.b.kind < PTL_FIELD_ZERO || f.b.kind > PTL_FIELD_CONFINED_DL)) {
+            ctx->err = "unknown field kind";
+            return PTL_EINVAL;
+        }
+        if (f.kind == PTL_FORCE_CHEB_CONTINUUM && (f.cheb_id < 0 || f.cheb_id >= (int)ctx->cls.size())) {
+            ctx->err = "forcing refers to a ChebContinuumLoss id that was never created";
+            return PTL_EHANDLE;
+        }
+    }
+    if (has_cb) {
+        for (int k = 0; k < cb->nwalls; k++) {
+            if (cb->wall[k].coord < 0 || cb->wall[k].coord > 2 || cb->wall[k].species < 0 || cb->wall[k].species >= PTL_NSPECIES) {
+                ctx->err = "wall callback: coord must be 0..2 and species a valid species id";
+                return PTL_EINVAL;
+            }
+        }
+    }
     if (has_cb) {
         for (int k = 0; k < cb->nwalls; k++) {
             int pi = (cb->wall[k].species >= 0 && cb->wall[k].species < PTL_NSPECIES) ? M.by_species[cb->wall[k].species] : -1;

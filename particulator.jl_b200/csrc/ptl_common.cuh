@@ -138,7 +138,7 @@ __device__ __forceinline__ double bits_to_u01(uint32_t lo, uint32_t hi) {
 
 // One Philox block as a real function: the advance kernels draw at ~70 sites and inlining the ten
 // rounds everywhere blew the kernel up to 300 KB of SASS (instruction-cache misses were the top stall).
-__device__ __noinline__ uint4 philox_block(uint32_t block, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, uint32_t k0, uint32_t k1) {
+static __device__ __noinline__ uint4 philox_block(uint32_t block, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, uint32_t k0, uint32_t k1) {
     uint32_t o[4];
     philox4x32_10(block, step, seed_lo, seed_hi, k0, k1, o);
     return make_uint4(o[0], o[1], o[2], o[3]);
@@ -179,8 +179,9 @@ struct Rng {
 __device__ __forceinline__ void child_uids(uint64_t parent, uint32_t idx, uint32_t step, uint32_t seed_lo, uint32_t seed_hi,
                                            uint64_t out[2]) {
     uint4 o = philox_block(idx, step, seed_lo, seed_hi, (uint32_t)parent, (uint32_t)(parent >> 32) ^ DOM_CHILD_UID);
-    out[0] = ((uint64_t)o.y << 32) | o.x;
-    out[1] = ((uint64_t)o.w << 32) | o.z;
+    // uid space: bit 63 set = hashed (births), clear = sequential (host-assigned); include/particulator_b200.h
+    out[0] = (((uint64_t)o.y << 32) | o.x) | PTL_UID_HASHED_BIT;
+    out[1] = (((uint64_t)o.w << 32) | o.z) | PTL_UID_HASHED_BIT;
 }
 
 }  // namespace ptl

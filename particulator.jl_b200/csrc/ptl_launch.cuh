@@ -1,0 +1,185 @@
+// ptl_launch.cuh — host-side launch logic of the advance kernels (kernel choice, grid sizing, shared-memory opt-in).
+// Included by ptl_adv_species.cu, which instantiates launch_advance_s for ONE species per translation unit.
+#pragma once
+#include "ptl_host.h"
+#include "ptl_advance.cuh"
+#include "ptl_advance_wf.cuh"
+#include "ptl_advance_bq.cuh"
+#include "ptl_advance_wq.cuh"
+
+#ifndef PTL_DEFAULT_LEPTON_KERNEL
+#define PTL_DEFAULT_LEPTON_KERNEL 3     // 3 = bq (list-scheduled), 5 = wq (warp-private pools)
+#endif
+
+namespace ptl_host {
+
+template <int SP, bool FIRST, bool CB>
+int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t smem, const long long* rows = nullptr) {
+    auto kern = k_advance<SP, FIRST, CB>;
+    // Function attributes are per DEVICE and this library may hold contexts on several devices in one process (and be
+    // driven from several host threads): set the opt-in on every launch (a cheap driver call) instead of once per process.
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, ADV_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long tiles = (i1 - i0 + 31) / 32;
+    long long want = (tiles + (ADV_THREADS / 32) - 1) / (ADV_THREADS / 32);
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
+// wavefront variant (collision-dominated species): persistent CTAs, shared-memory particle pool
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows) {
+    auto kern = k_advance_wf<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    (void)table_smem;
+    size_t smem = wf_pool_bytes() + tsm + 32;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);   // per device: see launch_advance_t
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WF_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long nrow = i1 - i0;
+    long long want = (nrow + WF_THREADS - 1) / WF_THREADS;
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
+// list-scheduled variant (incremental per-class lists, one barrier per round, two chunks per warp)
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_bq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, const long long* rows) {
+    auto kern = k_advance_bq<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    size_t smem = BQ_POOL_BYTES + tsm + 32;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);   // per device: see launch_advance_t
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, BQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    long long nrow = i1 - i0;
+    long long want = (nrow + BQ_SLOTS - 1) / BQ_SLOTS;
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, BQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
+// warp-private variant (round 2): every warp owns WQ_NS slots; no CTA barrier, no shared lists
+template <int SP, int TK, bool FIRST, bool CB>
+int32_t launch_advance_wq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, const long long* rows) {
+    auto kern = k_advance_wq<SP, TK, FIRST, CB>;
+    const TableView& TV = A.tab[SP];
+    size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
+    if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
+    size_t smem = WQ_POOL_BYTES + tsm + 32;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);   // per device: see launch_advance_t
+    int blocks_per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
+        blocks_per_sm = 1;
+    // Small passes (newborns, the reference's 1e4-electron swarms) are bound by the sequential chain of one particle,
+    // not by throughput: spread the rows over as many warps as have at least one full chunk of them.
+    long long nrow = i1 - i0;
+    long long want = (nrow + 32 * WQ_WARPS - 1) / (32 * WQ_WARPS);
+    long long grid = (long long)ctx->sm_count * blocks_per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+    kern<<<(unsigned)grid, WQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    LAUNCHED();
+    ctx->stats.launches++;
+    return 0;
+}
+
+template <int SP, bool FIRST, bool CB>
+int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, size_t table_smem, const long long* rows = nullptr) {
+    // PTL_KERNEL=wq: warp-private pools (k_advance_wq); bq: list-scheduled kernel (k_advance_bq); wf: the re-sorting kernel
+    // — kept for A/B measurements and run against each other by the parity tests.
+    const int variant = ctx->lepton_kernel ? ctx->lepton_kernel : PTL_DEFAULT_LEPTON_KERNEL;
+    if (variant == 5) {
+        if (A.tab[SP].kind == 0) return launch_advance_wq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, rows);
+        return launch_advance_wq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, rows);
+    }
+    if (variant != 4) {
+        if (A.tab[SP].kind == 0) return launch_advance_bq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, rows);
+        return launch_advance_bq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, rows);
+    }
+    if (A.tab[SP].kind == 0) return launch_advance_wf_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
+    return launch_advance_wf_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, table_smem, rows);
+}
+
+// First-pass kernel choice.  Photons, and any species whose measured kappa (sub-steps per row of the previous advance)
+// is small, are HBM-bound: free flights go through the streaming kernel and only the rows that collide within dt are
+// deferred, through an index list, to the general kernel of the species (one particle per lane for photons, wavefront
+// for leptons).  Collision-dominated populations go straight to the wavefront kernel.
+template <int SP>
+int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, bool first, bool cb, size_t smem, bool low_kappa) {
+    const long long* rows = nullptr;
+    if ((SP == PTL_PHOTON || low_kappa) && !cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->use_stream) {
+        size_t need = (size_t)(i1 - i0);
+        if (need > ctx->slow_cap) {
+            cudaFree(ctx->d_slow_rows);
+            ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
+            // grow geometrically (x2, at least 4 Mi entries): a photon population that grows every step must not pay a
+            // cudaFree/cudaMalloc pair inside most advance! calls (each one synchronises the device)
+            size_t cap = need * 2 > ((size_t)4 << 20) ? need * 2 : ((size_t)4 << 20);
+            CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
+            ctx->slow_cap = cap;
+        }
+        CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
+        const TableView& TV = A.tab[SP];
+        size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
+        long long pairs = (i1 - i0 + 1) / 2;
+        long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
+        long long maxgrid = (long long)ctx->sm_count * 8;
+        if (grid > maxgrid) grid = maxgrid;
+        bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
+        if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
+        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+        else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
+        if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+        LAUNCHED();
+        ctx->stats.launches++;
+        rows = ctx->d_slow_rows;
+        cb = false;
+    }
+    if constexpr (SP == PTL_PHOTON) {
+        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
+    } else {
+        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
+    }
+}
+
+}  // namespace ptl_host

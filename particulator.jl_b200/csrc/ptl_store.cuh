@@ -24,6 +24,21 @@ __global__ void k_fill_uid(uint64_t* __restrict__ uid, unsigned long long base, 
     if (i < n) uid[i] = base + (unsigned long long)i;
 }
 
+// largest sequential uid (bit 63 clear) of an uploaded uid column -> *out (atomicMax): keeps the context's default-uid
+// counter ahead of every live sequential uid without a host pass over the array
+static __global__ void k_uid_max(const uint64_t* __restrict__ uid, long long n, unsigned long long* out) {
+    unsigned long long m = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long u = uid[i];
+        if (!(u & PTL_UID_HASHED_BIT) && u > m) m = u;
+    }
+    for (int off = 16; off > 0; off >>= 1) { unsigned long long o = __shfl_down_sync(0xffffffffu, m, off); m = o > m ? o : m; }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// OR a bit-set into the sticky flags word from the host side (ptl_population_append on a full population)
+static __global__ void k_or_flags(int* flags, int bits) { atomicOr(flags, bits); }
+
 // ---- K2: droplow! (population.jl:273-284) + repack! (:229-259) ---------------------------------------------
 // repack! is a serial tail-fill: holes of the prefix are filled, in ascending order, by the actives of the
 // tail taken in descending order.  Parallel form: L' = #actives; holes h_1<h_2<.. among rows

@@ -9,7 +9,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import DiagOut, dptr, as_f64
+from ._lib import PtlError, DiagOut, dptr, as_f64
 from . import constants as co
 from .processes import ELECTRON, PHOTON, POSITRON, SLOW_ELECTRON
 
@@ -162,8 +162,12 @@ def empty(popl):
 def add_particle(popl, x, p, w=1.0, t=0.0, s=None, r=0.0, uid=0):
     s = -math.log(1.0 - np.random.random()) if s is None else s
     x, p = as_f64(x), as_f64(p)
-    j = popl.ctx.backend.population_append(popl.ctx.h, popl.id, dptr(x), dptr(p), w, t, s, r, int(uid))
-    return int(j)
+    j = int(popl.ctx.backend.population_append(popl.ctx.h, popl.id, dptr(x), dptr(p), w, t, s, r, int(uid)))
+    if j == -7:       # PTL_ECAPACITY: the reference asserts n < length(particles) (population.jl:107)
+        raise PtlError("add_particle!: population is full (CAPACITY_OVERFLOW)")
+    if j < -1:        # -1 alone means "below the energy cut, not added" (population.jl:105)
+        popl.ctx.check(j, "population_append")
+    return j
 
 
 def remove_particle(popl, i):

@@ -38,7 +38,7 @@ def test_python_binding_covers_the_header():
 def test_oracle_exports_the_same_abi():
     from oracle_backend import oracle_backend
     b = oracle_backend()
-    for s in P.ABI_SYMBOLS:
+    for s in P.ABI_SYMBOLS_CORE:
         assert hasattr(b.dll, "ora_" + s)
 
 
