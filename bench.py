@@ -7,7 +7,10 @@ electrons with E ~ exp(-E/7.3 MeV) on [1 keV, 100 MeV], cos(theta_z) ~ U[0.8, 1]
 positron populations start empty.  One "step" = what run! does per dt (src/run.jl:6-9): advance!(mpopl, pusher, t+dt)
 followed by droplow! on every population.  A particle-step = one particle alive at the start of a step carried
 through it.  Per-GPU work is fixed (weak scaling): N GPUs hold N x n_per_gpu electrons, sharded with no
-data-path collective; NCCL only reduces the diagnostics at the end.
+data-path collective; every rank uses the SAME seed (streams are keyed by particle uid, so results do not depend on the
+number of GPUs).  At N > 1 a second, strong-scaling measurement runs the named 1e8-electron avalanche split over the N
+GPUs with the library's NCCL collectives inside the timed region (`strong`): ptl_diag_allreduce every step (what run!
+prints, src/run.jl:31-40) and ptl_rebalance every second step.
 
   value     whole-job particle-steps/s, state resident in HBM (timed with CUDA events, max over ranks)
   e2e       the same through the C-ABI with HOST buffers: pinned host arrays -> ptl_population_upload ->
@@ -16,6 +19,9 @@ data-path collective; NCCL only reduces the diagnostics at the end.
              / its cudaEvent duration, against the measured HBM copy bandwidth
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm, OpenMP over all host cores) on a bounded
             sample of the same workload — a reported baseline, not the target
+  secondary the other BASELINE.json configurations and the latency regime, a few steps each (N = 1 only): photon
+            streaming, kappa ~ 1 electrons, the mixed e-/gamma/e+ population (configs[3]), the LXCat slow-electron swarm
+            with 64 channels (configs[4]), and the step latency of a 1e4-electron swarm (configs[0] size)
 `--impl reference` times that CPU restatement alone (Julia is not installable in this image)."""
 import argparse
 import json
@@ -206,6 +212,184 @@ def cpu_leg(P, tables, n_sample, steps, warmup, seed=0):
             "kappa": sub / max(psteps, 1), "substeps_per_s": sub / el_t, "ms_per_step": 1e3 * el_t / max(len(times), 1)}
 
 
+def _timed_steps(torch, P, mp, pops, psh, dt, steps, warmup, t0=0.0):
+    """`steps` timed steps (advance! + droplow! per step) after `warmup`; returns device ms, particle-steps, sub-steps, stats."""
+    t = t0
+    ms = 0.0
+    psteps = sub = 0
+    kern_ms = kern_rows = 0.0
+    per = []
+    st = None
+    for it in range(warmup + steps):
+        n0 = sum(len(q) for q in pops)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t += dt
+        P.advance(mp, psh, t)
+        st = P.last_advance_stats(mp)
+        for q in mp:
+            P.droplow(q)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            m = e0.elapsed_time(e1)
+            ms += m; psteps += n0; sub += st["substeps"]; kern_ms += st["main_ms"]; kern_rows += st["main_rows"]; per.append(round(m, 3))
+    return {"ms": ms, "psteps": psteps, "substeps": sub, "kern_ms": kern_ms, "kern_rows": kern_rows, "per_step_ms": per,
+            "passes": st["passes"] if st else 0, "t": t}
+
+
+def _probe_record(r, steps, peak, extra=None):
+    out = {"particle_steps_per_s": r["psteps"] / (r["ms"] * 1e-3), "substeps_per_s": r["substeps"] / (r["ms"] * 1e-3),
+           "kappa": r["substeps"] / max(r["psteps"], 1), "ms_per_step": r["ms"] / steps, "steps": steps, "passes_last_step": r["passes"],
+           "hbm_frac_whole_step": ALGO_BYTES_PER_PARTICLE_STEP * r["psteps"] / (r["ms"] * 1e-3) / 1e9 / peak,
+           "main_kernel_ms": r["kern_ms"] / steps,
+           "hbm_frac_main_kernel": (ALGO_BYTES_PER_PARTICLE_STEP * r["kern_rows"] / (r["kern_ms"] * 1e-3) / 1e9 / peak) if r["kern_ms"] > 0 else None}
+    out.update(extra or {})
+    return out
+
+
+def secondary_probes(torch, P, tables, peak, scale=1.0):
+    """The other BASELINE.json configurations, a few device-timed steps each, every one with its HBM fraction
+    (algorithmic 162 B per particle-step against the measured copy bandwidth) for the whole step and for the dominant kernel."""
+    co = P.co
+    out = {"note": "device-timed advance!+droplow! per step, populations resident in HBM, 3 timed steps after 2 warm-up steps; "
+                   "hbm_frac_* = 162 B x particle-steps / time / measured HBM peak"}
+    stream = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(11)
+
+    def directions(n, cmin=-1.0):
+        cost = rng.uniform(cmin, 1, n); phi = rng.uniform(0, 2 * np.pi, n); sint = np.sqrt(1 - cost ** 2)
+        return np.stack([sint * np.cos(phi), sint * np.sin(phi), cost], axis=1)
+
+    def state(sp, K, d):
+        return dict(x=np.zeros((len(K), 3)), p=d * P.momentum_norm_from_kin(sp, K)[:, None], s=-np.log(1 - rng.random(len(K))))
+
+    def world(ctx, ne, ng, npos, st_e=None, st_g=None, st_p=None, tabs=tables):
+        el = P.Population(ctx, P.ELECTRON, int(1.8 * ne) + (1 << 18), st_e, tabs["electron"], 1e3 * co.eV)
+        ph = P.Population(ctx, P.PHOTON, int(1.5 * ng) + (1 << 20), st_g, tabs["photon"], 1e3 * co.eV)
+        po = P.Population(ctx, P.POSITRON, int(4 * npos) + (1 << 18), st_p, tabs["positron"], 1e2 * co.eV)
+        return P.MultiPopulation(("electron", el), ("photon", ph), ("positron", po)), el, ph, po
+
+    psh = pusher(P)
+    # (1) photons only: the clean HBM-roofline measurement (BASELINE.md section 6 #4)
+    n = max(int(20_000_000 * scale), 4096)
+    ctx = P.Context(device=torch.cuda.current_device(), stream=stream); ctx.set_profiling(True)
+    Kg = np.exp(rng.uniform(np.log(1e4), np.log(3e7), n)) * co.eV
+    mp, el, ph, po = world(ctx, 1 << 20, n, 1 << 16, st_g=state(P.PHOTON, Kg, directions(n)))
+    r = _timed_steps(torch, P, mp, (ph,), psh, DT, 3, 2)
+    out["photon_streaming"] = _probe_record(r, 3, peak, {"workload": f"{n} photons, E ~ 1/E on [10 keV, 30 MeV], isotropic; secondaries advanced in the same step",
+                                                         "kernel": "k_advance_stream<photon>"})
+    ctx.close()
+    # (2) electrons at kappa ~ 1 (dt scaled down): where HBM binds for leptons
+    n = max(int(10_000_000 * scale), 4096)
+    dt1 = DT / 2048
+    ctx = P.Context(device=torch.cuda.current_device(), stream=stream); ctx.set_profiling(True)
+    Fdt = co.elementary_charge * EFIELD * dt1
+    tabs1 = dict(tables); tabs1["electron"] = P.build_electron_collision_table(P.air_composition(), Fdt, safety=1.15)
+    mp, el, ph, po = world(ctx, 2 * n, n // 4, n // 16, tabs=tabs1)
+    synth_electrons_device(torch, P, el, n, seed=7, uid0=1)
+    r = _timed_steps(torch, P, mp, (el,), psh, dt1, 3, 3)
+    out["electrons_kappa1"] = _probe_record(r, 3, peak, {"workload": f"{n} RREA electrons, dt = {dt1:.3e} s", "kernel": "k_advance_stream<electron>"})
+    ctx.close()
+    # (3) mixed feedback population, BASELINE configs[3]
+    ne = ng = max(int(10_000_000 * scale), 4096); npos = max(int(200_000 * scale), 512)
+    ctx = P.Context(device=torch.cuda.current_device(), stream=stream); ctx.set_profiling(True)
+    Ke = np.clip(rng.exponential(7.3e6, ne), 1e3 * 1.0001, 1e8) * co.eV
+    Kg = np.exp(rng.uniform(np.log(1e4), np.log(3e7), ng)) * co.eV
+    Kp = np.exp(rng.uniform(np.log(1e5), np.log(2e7), npos)) * co.eV
+    mp, el, ph, po = world(ctx, ne, ng, npos, state(P.ELECTRON, Ke, directions(ne, 0.8)), state(P.PHOTON, Kg, directions(ng)),
+                           state(P.POSITRON, Kp, directions(npos)))
+    r = _timed_steps(torch, P, mp, (el, ph, po), psh, DT, 3, 2)
+    out["mixed_config4"] = _probe_record(r, 3, peak, {"workload": f"{ne} e- + {ng} gamma + {npos} e+, all nine processes (BASELINE configs[3])",
+                                                      "flags": int(ctx.error_flags())})
+    ctx.close()
+    # (4) LXCat slow-electron swarm, 64 channels, BASELINE configs[4]
+    n = max(int(10_000_000 * scale), 4096)
+    ctx = P.Context(device=torch.cuda.current_device(), stream=stream); ctx.set_profiling(True)
+    tab = P.synthetic_lxcat_table(grid_kind=0, extra_levels=57)
+    stt = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * co.eV / co.electron_mass) * 1.2, s=-np.log(1 - rng.random(n)))
+    pop = P.Population(ctx, P.SLOW_ELECTRON, int(1.5 * n), stt, tab, 0.0)
+    mps = P.MultiPopulation(("slow", pop))
+    pshs = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -100 * co.Td * co.nair]), None))
+    r = _timed_steps(torch, P, mps, (pop,), pshs, 1e-12, 3, 2)
+    out["lxcat64_config5"] = _probe_record(r, 3, peak, {"workload": f"{n} slow electrons, Maxwellian 2 eV, 100 Td, dt = 1e-12 s, {len(tab.proc)} channels on a linear table",
+                                                        "kernel": "k_advance_wq<slow_electron, linear>"})
+    ctx.close()
+    # (5) latency regime: the reference's own working size (scripts/swarm.jl:29-30 keeps 1e4 electrons)
+    n = 10_000
+    ctx = P.Context(device=torch.cuda.current_device(), stream=stream); ctx.set_profiling(True)
+    mp, el, ph, po = world(ctx, 1 << 18, 1 << 18, 1 << 16)
+    synth_electrons_device(torch, P, el, n, seed=3, uid0=1)
+    r = _timed_steps(torch, P, mp, (el,), psh, DT, 5, 3)
+    out["swarm_1e4_latency"] = _probe_record(r, 5, peak, {"workload": "1e4 RREA electrons (the reference keeps its swarm at 1e4 electrons by roulette)",
+                                                          "per_step_ms": r["per_step_ms"]})
+    ctx.close()
+    return out
+
+
+def strong_leg(torch, dist, P, ctx, mp, el, psh, args, rank, world, barrier):
+    """BASELINE configs[2] as named: 1e8 electrons in TOTAL, split over the N GPUs (slightly unevenly, so that the rebalance
+    moves rows), with the library's NCCL collectives inside the timed region."""
+    from particulator_b200 import dist as pdist
+    total = args.strong_total
+    share = [1.0 + 0.2 * ((r / (world - 1)) - 0.5) for r in range(world)]          # +-10 % around the mean
+    counts = [int(total * sh / sum(share)) for sh in share]
+    n = counts[rank]
+    synth_electrons_device(torch, P, el, n, seed=4321 + rank, uid0=1 + rank * (1 << 40))
+    t = 100.0 * DT            # any start time: t is a per-particle column, set below
+    column_tensor(torch, el, 7, n).fill_(t)
+    steps, warmup = max(args.steps, 1), max(args.warmup, 1)
+    coll_ms = 0.0
+    moved_rows = 0
+    psteps = 0
+
+    def one(it, timed):
+        nonlocal t, coll_ms, moved_rows, psteps
+        n0 = len(el)
+        t += DT
+        P.advance(mp, psh, t)
+        for q in mp:
+            P.droplow(q)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        d = pdist.diag_allreduce(el)                      # global counts / moments every step (run.jl:31-40)
+        if it % 2 == 1:
+            _, mv = pdist.rebalance_device(el, tolerance=0.02)
+            if timed:
+                moved_rows += abs(mv)
+        c1.record()
+        torch.cuda.synchronize()
+        if timed:
+            coll_ms += c0.elapsed_time(c1)
+            psteps += n0
+        return d
+
+    for it in range(warmup):
+        one(it, False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    d = None
+    for it in range(steps):
+        d = one(warmup + it, True)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1), coll_ms], device="cuda", dtype=torch.float64)
+    tot = torch.tensor([float(psteps), float(moved_rows), float(len(el))], device="cuda", dtype=torch.float64)
+    nmax = torch.tensor([float(len(el))], device="cuda", dtype=torch.float64)
+    nmin = nmax.clone()
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+    return {"scaling": "strong", "electrons_total": total, "electrons_per_gpu_start": counts, "steps": steps,
+            "value": float(tot[0]) / (float(ms[0]) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(ms[0]) / steps,
+            "collective_ms_per_step": float(ms[1]) / steps, "rebalanced_rows_per_step": float(tot[1]) / 2 / steps,
+            "global_n_from_diag_allreduce": int(d.n), "global_n_from_sum": int(tot[2]),
+            "n_per_gpu_end": {"max": int(nmax.item()), "min": int(nmin.item())},
+            "collectives": "ptl_diag_allreduce every step + ptl_rebalance (tolerance 2 %) every second step, NCCL called from the library, inside the timed region"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,7 +400,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--strong-total", type=int, default=int(os.environ.get("PTL_BENCH_STRONG_TOTAL", 100_000_000)))
+    ap.add_argument("--secondary-scale", type=float, default=1.0, help="scale the secondary probe populations (tests use < 1)")
     ap.add_argument("--e2e-shards", type=int, default=int(os.environ.get("PTL_E2E_SHARDS", 12)))
     ap.add_argument("--e2e-workers", type=int, default=int(os.environ.get("PTL_E2E_WORKERS", 3)))
     args = ap.parse_args()
@@ -269,8 +458,12 @@ def main():
     cap_e = int(1.6 * n) + 4096       # room for the in-step births (~10 %) and the quasi-steady keV secondaries
     mp, el, ph, po = make_world(P, ctx, tables, cap_e, max(n // 2, 1 << 20), max(n // 16, 1 << 18))
     uid0 = 1 + rank * (1 << 40)
-    synth_electrons_device(torch, P, el, n, seed=1234 + rank, uid0=uid0)
-    ctx.set_rng(rank, 0)           # uid-keyed Philox: shards are independent through their uids; seed also differs
+    synth_electrons_device(torch, P, el, n, seed=1234 + rank, uid0=uid0)      # (the synthetic INPUT differs per rank; the RNG seed does not)
+    ctx.set_rng(0, 0)              # ONE seed for the whole job: Philox streams are keyed by uid, so shards are independent through
+                                   # their disjoint uid ranges and the result does not depend on how many GPUs share the particles
+    if dist is not None:
+        from particulator_b200 import dist as pdist
+        pdist.init_comm(ctx, dist)                                            # NCCL communicator inside the library (ptl_comm_init)
     psh = pusher(P)
 
     def barrier():
@@ -345,7 +538,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_advance_bq<electron> (first pass)",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_advance_wq<electron> (first pass)",
                 "kernel_ms_per_launch": main_ms / max(args.steps, 1), "rows_per_launch": main_rows / max(args.steps, 1),
                 "algorithmic_bytes_per_row": ALGO_BYTES_PER_PARTICLE_STEP,
                 "note": "electrons in STP air do kappa collision sub-steps per particle-step; the kernel is instruction-issue bound, "
@@ -381,7 +574,7 @@ def main():
         for wk in range(nworkers):
             wctx = P.Context(device=local_rank)                       # own non-blocking stream
             wmp, wel, wph, wpo = make_world(P, wctx, tables, shard_cap, max(shard_cap // 3, 1 << 20), max(shard_cap // 16, 1 << 18))
-            wctx.set_rng(rank * 16 + wk + 1, 0)
+            wctx.set_rng(0, 0)
             workers.append((wctx, wmp, wel, psh.desc(wctx)))
         got_rows = [0] * nshards
         out_cap = [int(1.3 * (bounds[k + 1] - bounds[k])) + 4096 for k in range(nshards)]
@@ -450,7 +643,22 @@ def main():
     # ---- CPU baseline on the host cores of this box (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_leg(P, tables, args.cpu_sample, 2, 1)
+        cpu = cpu_leg(P, tables, args.cpu_sample, max(args.cpu_steps, 1), 1)
+
+    # ---- secondary: the other BASELINE configurations and the latency regime (rank 0, N = 1 only) ----
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_probes(torch, P, tables, peak, args.secondary_scale)
+        except Exception as exc:  # pragma: no cover  (a failed probe must not void the headline)
+            secondary = {"error": repr(exc)}
+
+    # ---- strong scaling with the collectives inside the timed region (N > 1 only) ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        for q in mp:
+            q.set_n(0)
+        strong = strong_leg(torch, dist, P, ctx, mp, el, psh, args, rank, world, barrier)
 
     if rank == 0:
         line = {"metric": "particle-steps/sec", "value": value, "unit": "particle-steps/s", "n_gpus": max(world, 1), "steps": args.steps,
@@ -459,7 +667,7 @@ def main():
                 "gpu_launches": int(launches_all), "roofline": roofline, "cpu_baseline": cpu,
                 "kappa": substeps_all / max(psteps_all, 1.0), "substeps_per_s": substeps_all / (elapsed_all * 1e-3),
                 "hbm_roofline_frac_whole_step": (ALGO_BYTES_PER_PARTICLE_STEP * value / max(world, 1)) / 1e9 / peak,
-                "host_ms_per_step": host_steps}
+                "host_ms_per_step": host_steps, "secondary": secondary, "strong": strong}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()

@@ -71,6 +71,37 @@ static __device__ __noinline__ double setr(const AdvanceParams& P, const SmemTab
     return own_ratebound<SP>(P, S, eng);
 }
 
+// Repeated below-cut sub-steps taken in blocks (used by every advance kernel; see the comment in ptl_advance_wf.cuh).
+// A particle that the field decelerated below energy_cut keeps its old r != 0: do_one_collision! returns before it draws
+// anything (collisions.jl:148-151), so the loop of mixed_population.jl:66-87 repeats the same dt = s/r push until tfinal or
+// until the energy is back above the cut.  Under the uniform-E fast path the kinetic energy is a convex function of time,
+// so "below the cut after j sub-steps" implies below the cut at every sub-step in between: take the j sub-steps as ONE RK2
+// step of j*dt (p exact up to rounding, x within the RK2 truncation error of the longer step, < 1e-10 relative), with t
+// and trem accumulated sub-step by sub-step so that they stay bit-identical, and halve j when the energy would cross
+// the cut so that the first test at or above the cut is still taken by the regular path on the reference's own time grid.
+// Takes at most ~max_work sub-steps per call; `more` tells whether further repeated sub-steps remain.
+template <int SP>
+__device__ __forceinline__ unsigned long long coast_below_cut(const AdvanceParams& P, Vec3& x, Vec3& p, double& t, double& trem, const double tnext,
+                                                              const double cut, const int max_work, bool& more) {
+    unsigned long long nsub = 0;
+    int M = 128, work = 0;
+    more = false;
+    while (M >= 1) {
+        double tr = trem, tt = t;
+        int j = 0;
+        for (; j < M && tr > DBL_EPS && tr > tnext; j++) { tr -= tnext; tt += tnext; }   // mixed_population.jl:66-68,86
+        if (j == 0) break;                                           // the final free flight belongs to the regular path
+        work += j;
+        Vec3 xc = x, pc = p;
+        double tdum = 0;
+        push<SP>(P, xc, pc, tdum, tnext * j);
+        if (!(kinenergy<SP>(pc) < cut)) { M = j >> 1; continue; }    // would reach the cut: halve (M == 0: the regular path takes it)
+        x = xc; p = pc; t = tt; trem = tr; nsub += (unsigned long long)j;
+        if (work >= max_work) { more = true; break; }
+    }
+    return nsub;
+}
+
 template <int SP, bool FIRST, bool CB>
 __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                          unsigned long long* tile_counter, const long long* __restrict__ rows,
@@ -214,6 +245,13 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
                         break;
                     }
                     }
+                } else if (!CB && SP != PTL_PHOTON && r != 0.0 && P.fast_force && trem - dt > tnext) {
+                    // below the cut with r != 0: the loop would repeat this same dt = s/r push; take the repeats in blocks
+                    trem -= dt;                              // :86 of the sub-step just taken
+                    nsub++;
+                    bool more;
+                    do { nsub += coast_below_cut<SP>(P, x, p, t, trem, tnext, cut, 1 << 20, more); } while (more);
+                    continue;
                 }
             }
             trem -= dt;                                      // :86

@@ -24,7 +24,8 @@ constexpr int WF_WARPS = WF_THREADS / 32;
 #define WF_MIN_BLOCKS 2
 #endif
 
-enum { WS_LOAD = 0, WS_STEP, WS_COULOMB, WS_RBEB, WS_IONFIN, WS_OTHER, WS_IDLE, WS_NCLASS };
+// (class 4 was a separate IONFIN unit in round 1; it is the second half of the asynchronous LOAD now)
+enum { WS_LOAD = 0, WS_STEP, WS_COULOMB, WS_RBEB, WS_LOADWAIT, WS_OTHER, WS_IDLE, WS_NCLASS };
 static_assert(WS_IDLE == 6 && WF_WARPS == 8, "the lane-parallel scheduler assumes 6 work classes x 8 warps");
 constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the shared-memory cumulative-rate table
 #ifdef WF_LINEAR_SELECT
@@ -40,7 +41,9 @@ constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 constexpr uint32_t WF_COAST = 0x400u;   // OTHER unit: no collision, take the repeated below-cut sub-steps in blocks
 
 // double columns of the shared-memory particle pool
-enum { WD_X0 = 0, WD_X1, WD_X2, WD_P0, WD_P1, WD_P2, WD_T, WD_S, WD_R, WD_TREM, WD_ENG, WD_SCR, WD_NCOL };
+// (round 1 also kept the collision energy and the sampled E2 here; they are recomputed / passed in registers now: 16 bytes
+// per slot buy a third slot per lane in the warp-private kernel at two CTAs per SM)
+enum { WD_X0 = 0, WD_X1, WD_X2, WD_P0, WD_P1, WD_P2, WD_T, WD_S, WD_R, WD_TREM, WD_NCOL };
 
 struct WfPool {
     double* d;              // [WD_NCOL][np]
@@ -91,22 +94,8 @@ static __device__ __noinline__ unsigned long long wf_coast_below_cut(const Advan
     Vec3 x = wf_get3(S, WD_X0, it), p = wf_get3(S, WD_P0, it);
     double t = WFD(WD_T, it), trem = WFD(WD_TREM, it);
     const double tnext = WFD(WD_S, it) * frcp(WFD(WD_R, it));       // same expression as the STEP unit (:67)
-    unsigned long long nsub = 0;
-    int M = 128, work = 0;
     bool more = false;
-    while (M >= 1) {
-        double tr = trem, tt = t;
-        int j = 0;
-        for (; j < M && tr > DBL_EPS && tr > tnext; j++) { tr -= tnext; tt += tnext; }   // mixed_population.jl:66-68,86
-        if (j == 0) break;                                           // the final free flight belongs to the STEP unit
-        work += j;
-        Vec3 xc = x, pc = p;
-        double tdum = 0;
-        push<SP>(P, xc, pc, tdum, tnext * j);
-        if (!(kinenergy<SP>(pc) < cut)) { M = j >> 1; continue; }    // would reach the cut: halve (M == 0: STEP takes it)
-        x = xc; p = pc; t = tt; trem = tr; nsub += (unsigned long long)j;
-        if (work >= 256) { more = true; break; }
-    }
+    const unsigned long long nsub = coast_below_cut<SP>(P, x, p, t, trem, tnext, cut, 256, more);
     if (nsub) {
         wf_put3(S, WD_X0, it, x); wf_put3(S, WD_P0, it, p);
         WFD(WD_T, it) = t; WFD(WD_TREM, it) = trem;
@@ -281,7 +270,18 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
 // One work unit of slot `it` (state word `sw`).  Shared by the barrier-synchronous kernel (k_advance_wf) and the
 // queue-driven kernel (k_advance_aq).  `ldmask` = lanes of this warp that execute a LOAD unit right now (they share one
 // atomic on the global row counter).
-template <int SP, int TK, bool FIRST, bool CB>
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// ALOAD (warp-private kernel only): the LOAD unit does not wait for the row — it issues cp.async copies of the twelve
+// column entries straight into the slot and parks the slot in class LOADWAIT; the warp goes on with other classes while
+// HBM answers (the synchronous LOAD was the one long-scoreboard stall of the kernel: 0.55-0.7 warps per issue), and the
+// LOADWAIT unit, run after a warp-wide cp.async.wait_all, finishes advance_init! on the arrived row.
+template <int SP, int TK, bool FIRST, bool CB, bool ALOAD = false>
 __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const TableView& T, const PopView& Q, const WfPool& S,
                                                 const SmemTable& TS, const double* tcum, const bool fastsel, const RngCtx rc,
                                                 const double cut, const int it, const uint32_t sw, const unsigned ldmask,
@@ -306,6 +306,18 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         long long i = i0 + (long long)base + __popc(ldmask & ltmask);
         if (i >= i1) { S.state[it] = WS_IDLE; break; }
         if (rows != nullptr) i = rows[i];
+        if (ALOAD) {
+            cp_async8(&WFD(WD_X0, it), Q.col[COL_X0] + i); cp_async8(&WFD(WD_X1, it), Q.col[COL_X1] + i); cp_async8(&WFD(WD_X2, it), Q.col[COL_X2] + i);
+            cp_async8(&WFD(WD_P0, it), Q.col[COL_P0] + i); cp_async8(&WFD(WD_P1, it), Q.col[COL_P1] + i); cp_async8(&WFD(WD_P2, it), Q.col[COL_P2] + i);
+            cp_async8(&WFD(WD_T, it), Q.col[COL_T] + i); cp_async8(&WFD(WD_S, it), Q.col[COL_S] + i);
+            if (!FIRST) cp_async8(&WFD(WD_R, it), Q.col[COL_R] + i);
+            cp_async8(&S.uid[it], Q.uid + i);
+            cp_async4(&S.c2[it], Q.active + (i & ~3LL));              // the aligned word that holds the row's active flag
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            S.row[it] = i;
+            S.state[it] = WS_LOADWAIT;
+            break;
+        }
         if (!Q.active[i]) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (mixed_population.jl:63)
         Vec3 x = {Q.col[COL_X0][i], Q.col[COL_X1][i], Q.col[COL_X2][i]};
         Vec3 p = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
@@ -316,6 +328,19 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                               : Q.col[COL_R][i];                           // advance_init!  mixed_population.jl:97-110
         WFD(WD_TREM, it) = P.tfinal - t;                                   // :65
         S.uid[it] = Q.uid[i]; S.row[it] = i;
+        S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
+        S.state[it] = WS_STEP | WF_VALID;
+        break;
+    }
+    // ------------------------------------------------------------------------------------------
+    case WS_LOADWAIT: {   // the row has arrived in the slot (the caller waited for the warp's cp.async groups)
+        const long long i = S.row[it];
+        if (((S.c2[it] >> (8 * (int)(i & 3))) & 0xffu) == 0u) { S.state[it] = WS_LOAD; break; }    // l.active || continue  (:63)
+        if (FIRST) {
+            const Vec3 p = wf_get3(S, WD_P0, it);
+            WFD(WD_R, it) = fastsel ? wf_setr_cheb3<SP>(P, T, TS.ratebound, cut, p) : setr<SP>(P, TS, p);   // advance_init!  :97-110
+        }
+        WFD(WD_TREM, it) = P.tfinal - WFD(WD_T, it);                       // :65
         S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
         S.state[it] = WS_STEP | WF_VALID;
         break;
@@ -422,7 +447,6 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                     if (!CB) {                          // xi consumed; the second half of the block stays cached for the sampler
                         S.idx[it] = sp_idx + 1; S.cblock[it] = sp_idx >> 1; S.c2[it] = sp_o2; S.c3[it] = sp_o3;
                     }
-                    WFD(WD_ENG, it) = eng;
                     uint32_t c = kind == PTL_PROC_COULOMB ? WS_COULOMB : (kind == PTL_PROC_RBEB ? WS_RBEB : WS_OTHER);
                     next = c | WF_VALID | ((uint32_t)jsel << 16);
                 }
@@ -466,7 +490,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         else philox4x32_10(b0, rc.step, rc.seed_lo, rc.seed_hi, k0, k1, bw[0]);
 #pragma unroll
         for (int m = 1; m <= NT; m++) philox4x32_10(b0 + m, rc.step, rc.seed_lo, rc.seed_hi, k0, k1, bw[m]);
-        double eng = WFD(WD_ENG, it);
+        double eng = kinenergy<SP>(wf_get3(S, WD_P0, it));      // same p, same function as the STEP unit's test: same bits
         double B = TS.procs[sw >> 16].par[0];
         RbebConsts k = rbeb_consts<true>(eng, B);
         double w = 0.0;
@@ -493,7 +517,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
 #else
         Rng rng;
         wf_load_rng(S, it, rng);
-        double eng = WFD(WD_ENG, it);
+        double eng = kinenergy<SP>(wf_get3(S, WD_P0, it));      // same p, same function as the STEP unit's test: same bits
         double B = TS.procs[sw >> 16].par[0];
         RbebConsts k = rbeb_consts(eng, B);
         double w;
@@ -507,34 +531,29 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         wf_store_rng(S, it, rng);
 #endif
         if (!acc) break;                  // stays an RBEB item: more trials next round
-        WFD(WD_SCR, it) = B * w;          // E2
-#ifdef WF_SPLIT_IONFIN
-        S.state[it] = WS_IONFIN | WF_VALID | (sw & 0xffff0000u);
-        break;
-#endif
         // the accepted lanes (~3/4) finish the ionisation in this unit: one scheduling round less per event.
         // (Chaining units further -- COULOMB or IONFIN straight into the next STEP -- halves the rounds but was
-        // measured 10% slower: the STEP part then runs at ~20 of 32 lanes instead of re-packed full chunks.)
-    }
-    // fallthrough
-    case WS_IONFIN: {   // rbeb.jl:58-80 after the sampler: kinematics, apply!(NewParticle), birth
-        Rng rng;
-        wf_load_rng(S, it, rng);
-        double eng = WFD(WD_ENG, it), E2 = WFD(WD_SCR, it);
-        double B = TS.procs[sw >> 16].par[0];
-        double E1 = eng - E2 - B;
-        if (!(E2 < E1)) atomicOr(P.flags, PTL_ERR_SAMPLER_INVARIANT);   // @assert E2 < E1  rbeb.jl:63
-        Vec3 p = wf_get3(S, WD_P0, it);
-        Outcome o;
-        const double ccut = P.pop[PTL_ELECTRON].present ? P.pop[PTL_ELECTRON].energy_cut : INFINITY;
-        ionization_products(rng, rc, p, eng, E1, E2, o, ccut);
-        wf_store_rng(S, it, rng);
-        wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
-        if (o.sp2 >= 0) {
-            uint64_t cu[2];
-            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-            long long i = S.row[it];
-            add_particle(P, PTL_ELECTRON, wf_get3(S, WD_X0, it), o.p2, Q.col[COL_W][i], WFD(WD_T, it), o.s2, cu[0]);
+        // measured 10% slower: the STEP part then runs at ~20 of 32 lanes instead of re-packed full chunks.  A separate
+        // IONFIN class, one more round per ionisation, was 10 % slower too and is gone.)
+        // rbeb.jl:58-80 after the sampler: kinematics, apply!(NewParticle), birth
+        {
+            Rng rng;
+            wf_load_rng(S, it, rng);
+            const double E2 = B * w;
+            double E1 = eng - E2 - B;
+            if (!(E2 < E1)) atomicOr(P.flags, PTL_ERR_SAMPLER_INVARIANT);   // @assert E2 < E1  rbeb.jl:63
+            Vec3 p = wf_get3(S, WD_P0, it);
+            Outcome o;
+            const double ccut = P.pop[PTL_ELECTRON].present ? P.pop[PTL_ELECTRON].energy_cut : INFINITY;
+            ionization_products(rng, rc, p, eng, E1, E2, o, ccut);
+            wf_store_rng(S, it, rng);
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
+            if (o.sp2 >= 0) {
+                uint64_t cu[2];
+                child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+                long long i = S.row[it];
+                add_particle(P, PTL_ELECTRON, wf_get3(S, WD_X0, it), o.p2, Q.col[COL_W][i], WFD(WD_T, it), o.s2, cu[0]);
+            }
         }
         break;
     }
@@ -549,7 +568,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         Rng rng;
         wf_load_rng(S, it, rng);
         Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
-        double eng = WFD(WD_ENG, it), t = WFD(WD_T, it);
+        double eng = kinenergy<SP>(p), t = WFD(WD_T, it);       // same p, same function as the STEP unit's test: same bits
         Outcome o;
         collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
         wf_store_rng(S, it, rng);

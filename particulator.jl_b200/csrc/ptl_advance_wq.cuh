@@ -23,16 +23,39 @@
 namespace ptl {
 
 #ifndef WQ_THREADS_MACRO
-#define WQ_THREADS_MACRO 256
+#define WQ_THREADS_MACRO 512
 #endif
 #ifndef WQ_K_MACRO
-#define WQ_K_MACRO 2                    // slots per lane
+#define WQ_K_MACRO 3                    // slots per lane
 #endif
 #ifndef WQ_MIN_BLOCKS
-#define WQ_MIN_BLOCKS 2
+#define WQ_MIN_BLOCKS 1
 #endif
 #ifndef WQ_AGE_SHIFT
-#define WQ_AGE_SHIFT 1                  // a class that was passed over gains (rounds waited << WQ_AGE_SHIFT) / 8 lanes of priority
+#define WQ_AGE_SHIFT 1                  // (autonomous mode) a class that was passed over gains (rounds waited << WQ_AGE_SHIFT) / 8 lanes of priority
+#endif
+#ifndef WQ_ALOAD
+#define WQ_ALOAD 0                      // 1: asynchronous LOAD (cp.async the row into the slot, finish it in a later round, class LOADWAIT).
+                                        // Measured on B200 (4e6 electrons): 29.9 ms against 28.2 ms for the plain LOAD — the extra, poorly filled
+                                        // LOADWAIT rounds cost more than the long-scoreboard stall they remove (other warps already hide it).
+#endif
+#ifndef WQ_LOAD_WEIGHT
+#define WQ_LOAD_WEIGHT 8                // score per pending LOAD / LOADWAIT entry (8 = like every other class)
+#endif
+#ifndef WQ_SYNC
+#define WQ_SYNC 0                       // 0: autonomous warps (default); 1: the warps of a group agree on one class per round (one barrier)
+#endif
+#ifndef WQ_GROUP
+#define WQ_GROUP (WQ_THREADS_MACRO / 32)   // (synchronous mode) warps that agree on one class per round; default: the whole CTA
+#endif
+#ifndef WQ_GROUP_STRIDED
+#define WQ_GROUP_STRIDED 0              // 1: group = warps with the same (warp id mod number of groups), i.e. one SM sub-partition each
+#endif
+#ifndef WQ_AGE_FORCE
+#define WQ_AGE_FORCE 12                 // rounds after which a waiting class becomes the CTA's top class whatever its size
+#endif
+#ifndef WQ_FOLLOW_SLACK
+#define WQ_FOLLOW_SLACK 12              // a warp follows the CTA's class unless its own best class has this many more lanes
 #endif
 constexpr int WQ_THREADS = WQ_THREADS_MACRO;
 constexpr int WQ_WARPS = WQ_THREADS / 32;
@@ -42,7 +65,7 @@ constexpr int WQ_SLOTS = WQ_NS * WQ_WARPS;          // slots per CTA
 static_assert(WQ_NS <= 255, "class populations are summed in 8-bit fields");
 
 constexpr size_t WQ_POOL_BYTES =
-    ((sizeof(double) * WD_NCOL * WQ_SLOTS + 16 * WQ_SLOTS + 4 * 5 * WQ_SLOTS + 2 * 32 * WQ_WARPS) + 15) / 16 * 16;
+    ((sizeof(double) * WD_NCOL * WQ_SLOTS + 16 * WQ_SLOTS + 4 * 5 * WQ_SLOTS + 2 * 32 * WQ_WARPS + 8 * 4 * 8) + 15) / 16 * 16;
 
 template <int SP, int TK, bool FIRST, bool CB>
 __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
@@ -103,42 +126,85 @@ __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const 
     unsigned long long nsub = 0;
     __syncthreads();                                                                // the table is staged; last CTA-wide barrier
 
-    // rounds a non-empty class has been passed over, 6 x 5 bits (saturating at 31)
-    unsigned age = 0;
+    // Scheduler state is lane-parallel: lane c (c < 6) owns class c — its population, its score, its age (rounds a
+    // non-empty class has been passed over).  Decisions are one REDUX each, so a round costs ~30 scheduler instructions
+    // next to the ~500 of a work unit (the first version evaluated every class in every lane: 22 % of all instructions).
+    int age = 0;
     unsigned round = 0;
+    const int myc = lane < WS_IDLE ? lane : 0;
+#if WQ_SYNC
+    // CTA-synchronous class choice.  With autonomous warps the 16 warps of an SM execute up to five different work units
+    // at the same time: the hot SASS (~30 KB for 99 % of the executed instructions, scattered over 158 KB) against a
+    // 32 KB instruction cache, and ncu showed the barrier stall of the list-scheduled kernel (2.3 warps per issue) simply
+    // replaced by instruction-fetch stalls (3.3; hit rate 73 %, profiles/r2_wq_async_ncu_summary.csv).  So the warps of a
+    // CTA agree on ONE class per round: every warp adds its (capped) class populations to a shared 64-bit counter, one
+    // barrier, everybody derives the same "top" class from the same totals, and a warp follows it unless its own pool
+    // is clearly better served by another class.  All warps then run the same straight-line unit at the same time
+    // (equal durations: the barrier wait is short, and the SM holds one or two units' code instead of five).
+    // The agreement group is WQ_GROUP warps: the whole CTA, or (WQ_GROUP_STRIDED) the warps that share one of the four
+    // SM sub-partitions (warp id mod 4 picks the scheduler), synchronised with a named barrier of their own.
+    constexpr int NGROUPS = WQ_WARPS / WQ_GROUP;
+    const int grp = WQ_GROUP_STRIDED ? (wid % NGROUPS) : (wid / WQ_GROUP);
+    unsigned long long* csum = reinterpret_cast<unsigned long long*>(order_all + 32 * WQ_WARPS) + 4 * grp;     // [group][3(+1)], 6 x 10-bit fields
+    if (tid < 4 * NGROUPS) reinterpret_cast<unsigned long long*>(order_all + 32 * WQ_WARPS)[tid] = 0ULL;
+    __syncthreads();
+    const bool grp_lead = WQ_GROUP_STRIDED ? (wid < NGROUPS) : (wid % WQ_GROUP == 0);
+#endif
     for (;; round++) {
+        // class populations of this warp's pool: every lane adds a one-hot byte per owned slot (class c -> byte c of a
+        // 64-bit word; retired slots land in the unused byte 6), two REDUX adds sum the halves over the warp
         uint32_t cls[WQ_K];
-        uint32_t pa = 0, pb = 0;
+        unsigned long long oh = 0;
 #pragma unroll
         for (int k = 0; k < WQ_K; k++) {
             cls[k] = S.state[base + 32 * k + lane] & 0xffu;
-            pa += cls[k] < 4u ? (1u << (8 * cls[k])) : 0u;                          // LOAD, STEP, COULOMB, RBEB
-            pb += (cls[k] == WS_IONFIN) ? 1u : (cls[k] == WS_OTHER ? 256u : 0u);
+            oh += 1ULL << (8 * cls[k]);
         }
-        pa = __reduce_add_sync(0xffffffffu, pa);
-        pb = __reduce_add_sync(0xffffffffu, pb);
-        if ((pa | pb) == 0u) break;                                                 // every slot of this warp is retired
-        // pick the class: most pending entries (capped at a full chunk) plus the age bonus; ties -> lower class
-        int best = 0, bscore = -1;
-#pragma unroll
-        for (int c = 0; c < WS_IDLE; c++) {
-            const int n = (int)(((c < 4 ? pa : pb) >> (8 * (c & 3))) & 0xffu);
-            const int a = (int)((age >> (5 * c)) & 31u);
-            const int score = n > 0 ? ((n < 32 ? n : 32) << 3) + (a << WQ_AGE_SHIFT) : -1;
-            if (score > bscore) { bscore = score; best = c; }
-        }
-        // ages: the picked class restarts, every other non-empty class waits one more round
+        const uint32_t pa = __reduce_add_sync(0xffffffffu, (uint32_t)oh);            // LOAD, STEP, COULOMB, RBEB
+        const uint32_t pb = __reduce_add_sync(0xffffffffu, (uint32_t)(oh >> 32)) & 0xffffu;   // LOADWAIT, OTHER
+        // lane c: population of class c in this warp's pool, capped at one chunk
+        const int n_c = lane < WS_IDLE ? (int)(((lane < 4 ? pa : pb) >> (8 * (lane & 3))) & 0xffu) : 0;
+        const int f_c = n_c < 32 ? n_c : 32;
+        int best;
+#if WQ_SYNC
         {
-            unsigned na = 0;
-#pragma unroll
-            for (int c = 0; c < WS_IDLE; c++) {
-                const unsigned n = ((c < 4 ? pa : pb) >> (8 * (c & 3))) & 0xffu;
-                unsigned a = (age >> (5 * c)) & 31u;
-                a = (c == best || n == 0u) ? 0u : (a < 31u ? a + 1u : 31u);
-                na |= a << (5 * c);
-            }
-            age = na;
+            const unsigned cb3 = round % 3;
+            // the six capped populations as 10-bit fields of one 64-bit word: low half = classes 0-2, high half = 3-5
+            const unsigned fld = (unsigned)f_c << (10 * (myc % 3));
+            const unsigned wlo = __reduce_add_sync(0xffffffffu, lane < 3 ? fld : 0u);
+            const unsigned whi = __reduce_add_sync(0xffffffffu, (lane >= 3 && lane < WS_IDLE) ? fld : 0u);
+            if (lane == 0 && (wlo | whi) != 0u) atomicAdd(csum + cb3, ((unsigned long long)whi << 32) | wlo);
+            if (NGROUPS == 1) __syncthreads();
+            else asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(32 * WQ_GROUP) : "memory");
+            const unsigned long long tot = csum[cb3];
+            if (grp_lead && lane == 0) csum[(cb3 + 2) % 3] = 0ULL;      // read two barriers ago, added to after the next barrier
+            if (tot == 0ULL) break;                                     // CTA-uniform: every slot of every warp is retired
+            // the CTA's top class: most runnable entries; a class that waited WQ_AGE_FORCE rounds goes first
+            const int N_c = lane < WS_IDLE ? (int)(((unsigned)(tot >> (32 * (myc / 3))) >> (10 * (myc % 3))) & 1023u) : 0;
+            const int tsc = N_c > 0 ? N_c + (age >= WQ_AGE_FORCE ? 4096 + (age << 8) : 0) : 0;
+            const unsigned tkey = __reduce_max_sync(0xffffffffu, ((unsigned)tsc << 3) | (unsigned)(7 - myc));
+            const int top = 7 - (int)(tkey & 7u);
+            const bool forced = (tkey >> 3) >= 4096u;
+            age = (lane == top || N_c == 0) ? 0 : (age < 31 ? age + 1 : 31);
+            // this warp: follow the CTA unless the own pool is clearly better served by another class
+            const unsigned okey = __reduce_max_sync(0xffffffffu, ((unsigned)f_c << 3) | (unsigned)(7 - myc));
+            const int oscore = (int)(okey >> 3);
+            if (oscore == 0) continue;                                  // nothing pending here: keep the barrier count, wait
+            const int ntop = __shfl_sync(0xffffffffu, f_c, top);
+            best = (ntop > 0 && (forced || ntop + WQ_FOLLOW_SLACK >= oscore)) ? top : 7 - (int)(okey & 7u);
         }
+#else
+        {
+            if ((pa | pb) == 0u) break;                                 // every slot of this warp is retired
+            // most pending entries (capped at a full chunk) plus the age bonus; ties -> lower class
+            // (LOAD / LOADWAIT units are short: they may run with fewer lanes, so that finished slots do not idle)
+            const int wgt = (lane == WS_LOAD || lane == WS_LOADWAIT) ? WQ_LOAD_WEIGHT : 8;
+            const int sc = n_c > 0 ? f_c * wgt + (age << WQ_AGE_SHIFT) : 0;
+            const unsigned key = __reduce_max_sync(0xffffffffu, ((unsigned)sc << 3) | (unsigned)(7 - myc));
+            best = 7 - (int)(key & 7u);
+            age = (lane == best || n_c == 0) ? 0 : (age < 31 ? age + 1 : 31);
+        }
+#endif
         // compact up to 32 slot ids of the picked class; the starting group rotates so that no slot waits forever when
         // its class stays above 32 entries
         int pos = 0;
@@ -158,10 +224,14 @@ __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const 
         const int cnt = pos < 32 ? pos : 32;
         const bool has = lane < cnt;
         const unsigned amask = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        if (WQ_ALOAD && best == WS_LOADWAIT) {        // rows requested by ANY lane of this warp have landed and are visible to all
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+        }
         if (has) {
             const int it = (int)order[lane];
             const uint32_t sw = S.state[it];
-            wf_execute_unit<SP, TK, FIRST, CB>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, amask, lane, ltmask, row_counter, i0, i1, nsub, rows);
+            wf_execute_unit<SP, TK, FIRST, CB, WQ_ALOAD != 0>(P, T, Q, S, TS, tcum, fastsel, rc, cut, it, sw, amask, lane, ltmask, row_counter, i0, i1, nsub, rows);
         }
         __syncwarp();
     }

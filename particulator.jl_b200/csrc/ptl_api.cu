@@ -64,6 +64,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
         ctx->lepton_kernel = !strcmp(km, "wq") ? 5 : (!strcmp(km, "bq") ? 3 : (!strcmp(km, "wf") ? 4 : 0));
         if (!strcmp(km, "nostream")) ctx->use_stream = false;
     }
+    if (const char* sp = getenv("PTL_SMALL_PASS")) ctx->small_pass_rows = atoll(sp);
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -140,6 +141,7 @@ EXPORT int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value)
         return 0;
     }
     if (!strcmp(name, "stream")) { ctx->use_stream = value != 0; return 0; }
+    if (!strcmp(name, "small_pass_rows")) { if (value < 0) return PTL_EINVAL; ctx->small_pass_rows = value; return 0; }
     ctx->err = std::string("unknown option ") + name;
     return PTL_EINVAL;
 }

@@ -98,6 +98,7 @@ struct ptl_context {
     long long* d_slow_rows = nullptr;  // rows the streaming photon kernel deferred to the general kernel
     size_t slow_cap = 0;
     int lepton_kernel = 0;             // 0 = default (PTL_DEFAULT_LEPTON_KERNEL), 3 = bq, 4 = wf, 5 = wq (ptl_set_option "kernel" / PTL_KERNEL)
+    long long small_pass_rows = 16384; // lepton passes with fewer rows run on the one-particle-per-lane kernel (chain latency, not throughput)
     bool use_stream = true;            // streaming fast path for low-kappa species (ptl_set_option "stream" / PTL_KERNEL=nostream)
     long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
     bool profiling = false;

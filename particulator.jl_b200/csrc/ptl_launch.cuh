@@ -8,7 +8,7 @@
 #include "ptl_advance_wq.cuh"
 
 #ifndef PTL_DEFAULT_LEPTON_KERNEL
-#define PTL_DEFAULT_LEPTON_KERNEL 3     // 3 = bq (list-scheduled), 5 = wq (warp-private pools)
+#define PTL_DEFAULT_LEPTON_KERNEL 5     // 3 = bq (list-scheduled, round 1), 5 = wq (warp-private pools, round 2)
 #endif
 
 namespace ptl_host {
@@ -100,7 +100,7 @@ int32_t launch_advance_wq_k(ptl_context* ctx, const AdvanceParams& A, long long 
     size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
     if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
     size_t smem = WQ_POOL_BYTES + tsm + 32;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);   // per device: see launch_advance_t
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    // per device: see launch_advance_t
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WQ_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
         blocks_per_sm = 1;
@@ -173,13 +173,19 @@ int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0,
         rows = ctx->d_slow_rows;
         cb = false;
     }
-    if constexpr (SP == PTL_PHOTON) {
-        if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
-        return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
-    } else {
-        if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
-        return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
+    // Small passes (the newborns of a step, the reference's own 1e4-electron swarms) are bound by the sequential chain of
+    // ONE particle (up to ~400 collisions within dt), not by throughput: the one-particle-per-lane kernel keeps the state
+    // in registers and has no scheduling rounds, so a chain runs ~2.5x faster there; the wavefront kernels win as soon as
+    // there are enough rows to fill the machine (ctx->small_pass_rows, ptl_set_option "small_pass_rows").
+    const bool small_pass = SP != PTL_PHOTON && rows == nullptr && (i1 - i0) < ctx->small_pass_rows;
+    if constexpr (SP != PTL_PHOTON) {
+        if (!small_pass) {
+            if (first) return cb ? launch_advance_wf_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+            return cb ? launch_advance_wf_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_wf_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
+        }
     }
+    if (first) return cb ? launch_advance_t<SP, true, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, true, false>(ctx, A, i0, i1, smem, rows);
+    return cb ? launch_advance_t<SP, false, true>(ctx, A, i0, i1, smem, rows) : launch_advance_t<SP, false, false>(ctx, A, i0, i1, smem, rows);
 }
 
 }  // namespace ptl_host

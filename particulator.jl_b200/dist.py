@@ -1,15 +1,79 @@
 """Multi-GPU plumbing: one process per GPU, particles sharded, NCCL only where the path has an exchange step.
 
 The reference has no distributed code at all; particles never interact, so every rank
-owns an independent shard of every species and advances it with no data-path collective.  Two collectives exist:
-  * `allreduce_diag`  — sum / max of the fused diagnostics (counts, weights, energy and position moments,
-    histograms) so that `nactives`, `meanenergy`, `spread`, ... report GLOBAL values (run.jl:31-40, callback.jl:203);
-  * `rebalance`       — periodic population rebalancing: all-gather of the per-rank counts, a deterministic
-    transfer plan, then point-to-point send/recv of column tails straight out of / into the library's device
-    columns (zero-copy through the CUDA array interface).
-`torch.distributed` is plumbing only (process group, NCCL); with the `gloo` backend and CPU tensors the same
-host logic is unit-tested without GPUs."""
+owns an independent shard of every species and advances it with no data-path collective.  Two collectives exist, and
+both live INSIDE the shared library (csrc/ptl_comm.cu, NCCL called from the C ABI) so that a Julia host can use them:
+  * `diag_allreduce` / `histogram_allreduce` / `allreduce` — sum / max of the fused diagnostics (counts, weights, energy
+    and position moments, spectra) so that `nactives`, `meanenergy`, `spread`, ... report GLOBAL values
+    (run.jl:31-40, callback.jl:203);
+  * `rebalance` — periodic population rebalancing: all-gather of the per-rank counts, a deterministic transfer plan,
+    ONE grouped ncclSend/ncclRecv of the 12 column tails straight out of / into the device-resident columns.
+This module is the thin host-side caller: `init_comm` ships the 128-byte NCCL id between ranks (through
+`torch.distributed` when that is the launcher, or any callable), the rest are one-line calls into the ABI.
+`plan_rebalance` / `exchange_columns` restate the host logic in Python over a `torch.distributed` group; with the `gloo`
+backend and CPU tensors they are the unit-testable mirror of what ptl_rebalance does (tests/test_dist_gloo.py)."""
+import ctypes as C
+
 import numpy as np
+
+from ._lib import DiagOut, dptr
+
+
+def init_comm(ctx, dist=None, rank=None, nranks=None, exchange=None):
+    """Attach an NCCL communicator to `ctx` (ptl_comm_init).  The id is created on rank 0 (ptl_comm_unique_id) and shipped
+    with `exchange(bytes_or_None) -> bytes` if given, else broadcast through the torch.distributed group `dist`."""
+    import numpy as _np
+    if dist is not None:
+        rank = dist.get_rank() if rank is None else rank
+        nranks = dist.get_world_size() if nranks is None else nranks
+    buf = _np.zeros(128, dtype=_np.uint8)
+    if rank == 0:
+        ctx.check(ctx.backend.comm_unique_id(buf.ctypes.data_as(C.POINTER(C.c_uint8))), "comm_unique_id")
+    if exchange is not None:
+        buf = _np.frombuffer(exchange(buf.tobytes() if rank == 0 else None), dtype=_np.uint8).copy()
+    elif dist is not None and nranks > 1:
+        import torch
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(buf).to(dev)
+        dist.broadcast(t, src=0)
+        buf = t.cpu().numpy().copy()
+    ctx.check(ctx.backend.comm_init(ctx.h, buf.ctypes.data_as(C.POINTER(C.c_uint8)), int(rank), int(nranks)), "comm_init")
+    return rank, nranks
+
+
+def destroy_comm(ctx):
+    ctx.check(ctx.backend.comm_destroy(ctx.h), "comm_destroy")
+
+
+def diag_allreduce(popl):
+    """ptl_diag with global sums / max over the communicator of the population's context."""
+    d = DiagOut()
+    popl.ctx.check(popl.ctx.backend.diag_allreduce(popl.ctx.h, popl.id, C.byref(d)), "diag_allreduce")
+    return d
+
+
+def histogram_allreduce(popl, quantity, lo, hi, nbins, logscale=False):
+    out = np.zeros(nbins)
+    q = {"energy": 0, "costheta": 1}[quantity]
+    popl.ctx.check(popl.ctx.backend.histogram_allreduce(popl.ctx.h, popl.id, q, float(lo), float(hi), nbins, 1 if logscale else 0,
+                                                        dptr(out)), "histogram_allreduce")
+    return out
+
+
+def allreduce(ctx, values, op="sum"):
+    """In-place all-reduce of a small host vector through the library's communicator."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    ctx.check(ctx.backend.comm_allreduce_f64(ctx.h, dptr(v), len(v), {"sum": 0, "max": 1, "min": 2}[op]), "comm_allreduce_f64")
+    return v
+
+
+def rebalance_device(popl, tolerance=0.05):
+    """ptl_rebalance: returns (n_after, rows sent (+) / received (-))."""
+    moved = C.c_int64(0)
+    n = int(popl.ctx.backend.rebalance(popl.ctx.h, popl.id, float(tolerance), C.byref(moved)))
+    popl.ctx.check(n, "rebalance")
+    return n, int(moved.value)
+
 
 NCOLS = 12      # x0,x1,x2,p0,p1,p2,w,t,s,r (f64) + active (u8) + uid (u64)
 

@@ -5,6 +5,5 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p build/ab
-cd particulator.jl_b200/csrc
-env -u CC -u CXX nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-fvisibility=hidden -shared --expt-relaxed-constexpr "$@" -o ../../build/ab/libptl_$name.so ptl_api.cu
+python particulator.jl_b200/build.py -o build/ab/libptl_$name.so "$@" >/dev/null
 echo built build/ab/libptl_$name.so

@@ -36,10 +36,15 @@ def octx():
     ctx.close()
 
 
-@pytest.fixture()
-def gctx():
-    """CUDA context.  No fallback: if the library or the device is missing the test FAILS."""
+@pytest.fixture(params=["wavefront", "default"])
+def gctx(request):
+    """CUDA context.  No fallback: if the library or the device is missing the test FAILS.
+    Every GPU test runs twice: with the wavefront lepton kernel forced for every pass ("wavefront": small_pass_rows = 0, so
+    that test-sized populations exercise the kernel the benchmark runs), and with the library's default dispatch, which sends
+    passes of fewer than 16384 rows to the one-particle-per-lane kernel."""
     ctx = P.Context(device=0)
+    if request.param == "wavefront":
+        ctx.set_option("small_pass_rows", 0)
     yield ctx
     ctx.close()
 

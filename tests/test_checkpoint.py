@@ -28,9 +28,11 @@ def _roundtrip(make_ctx, air_tables, tmp_path):
     a.set_rng(7, 0)
     mpa, *pa = make_world(a, air_tables, 600, 400, 50, cap=20000, seed=4)
     ta = _steps(mpa, pa, 0.0, 2)
-    path = str(tmp_path / "state.npz")
+    path = str(tmp_path / "state.ckpt")         # no .npz suffix: the name must be used verbatim (np.savez would append one)
     meta = checkpoint.save_checkpoint(path, mpa, ta, extra={"note": "after 2 steps"})
+    assert (tmp_path / "state.ckpt").exists()
     assert meta["step"] == a.get_rng()[1] and meta["seed"] == 7
+    assert meta["next_uid"] == a.get_uid_counter() > 1
     blob = checkpoint.dumps(mpa, ta)
     ta = _steps(mpa, pa, ta, 2)                 # uninterrupted run continues
 
@@ -39,6 +41,11 @@ def _roundtrip(make_ctx, air_tables, tmp_path):
     mpb, *pb = make_world(b, air_tables, 0, 0, 0, cap=20000, seed=0)
     tb = checkpoint.load_checkpoint(path, mpb)
     assert tb == pytest.approx(2 * DT) and b.get_rng() == (7, meta["step"])
+    # the uid counter survives: a particle injected after the restore gets a uid no live particle has (uids key the RNG)
+    assert b.get_uid_counter() >= meta["next_uid"]
+    live = np.concatenate([q.download()["uid"] for q in pb])
+    seq = live[(live >> np.uint64(63)) == 0]
+    assert b.get_uid_counter() > int(seq.max())
     tb = _steps(mpb, pb, tb, 2)
     assert ta == tb
     for qa, qb in zip(pa, pb):
@@ -73,3 +80,25 @@ def test_checkpoint_rejects_foreign_files(tmp_path):
     np.savez(p, meta=np.frombuffer(b'{"format": "other"}', dtype=np.uint8))
     with pytest.raises(ValueError):
         checkpoint.read_checkpoint(str(p))
+
+
+def test_restore_without_saved_counter_still_avoids_live_uids(air_tables):
+    """Explicit uids move the default-uid counter past the largest sequential uid (a restored context used to
+    restart at 1 + sum(n) and could reissue a live uid)."""
+    ctx = oracle_context()
+    mp, el, ph, po = make_world(ctx, air_tables, 50, 0, 0, cap=1000, seed=1)    # uids 1..50 (explicit, conftest)
+    assert ctx.get_uid_counter() == 51
+    j = P.add_particle(el, [0, 0, 0], [0, 0, 3e-22], uid=0)
+    assert j == 50 and int(el.download()["uid"][50]) == 51
+    ctx.close()
+
+
+def test_load_rejects_populations_missing_from_the_file(air_tables, tmp_path):
+    a = oracle_context()
+    mpa, ela, pha, poa = make_world(a, air_tables, 10, 0, 0, cap=100, seed=1)
+    one = P.MultiPopulation(("electron", ela))
+    path = str(tmp_path / "only_e.ckpt")
+    checkpoint.save_checkpoint(path, one, 0.0)
+    with pytest.raises(KeyError):
+        checkpoint.load_checkpoint(path, mpa)      # photon / positron populations are not in the file
+    a.close()

@@ -32,6 +32,28 @@ def test_plan_rebalance_properties():
     assert plan_rebalance([10, 0]) == [(0, 1, 5)]
 
 
+def test_c_abi_plan_equals_python_plan():
+    """ptl_rebalance_plan (the plan ptl_rebalance executes over NCCL, pure host code in the CUDA library) against the Python
+    statement of the same greedy matching."""
+    import ctypes as C
+    import particulator_b200 as P
+    from particulator_b200.dist import plan_rebalance
+    dll = C.CDLL(P.LIB_PATH)
+    f = dll.ptl_rebalance_plan
+    f.restype = C.c_int32
+    f.argtypes = [C.POINTER(C.c_int64), C.c_int32, C.c_double, C.POINTER(C.c_int64), C.c_int32]
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        n = int(rng.integers(1, 17))
+        counts = np.ascontiguousarray(rng.integers(0, 10 ** int(rng.integers(1, 9)), n), dtype=np.int64)
+        tol = float(rng.choice([0.0, 0.05, 0.5]))
+        moves = np.zeros(3 * n, dtype=np.int64)
+        m = f(counts.ctypes.data_as(C.POINTER(C.c_int64)), n, tol, moves.ctypes.data_as(C.POINTER(C.c_int64)), n)
+        assert m >= 0
+        got = [tuple(int(v) for v in moves[3 * q:3 * q + 3]) for q in range(m)]
+        assert got == plan_rebalance([int(c) for c in counts], tol), (counts, tol)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

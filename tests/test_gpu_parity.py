@@ -591,6 +591,7 @@ def test_lepton_kernel_variants_are_bit_identical(gctx, air_tables, variant):
         ctx = P.Context(device=0)
         try:
             ctx.set_option("kernel", kernel)
+            ctx.set_option("small_pass_rows", 0)      # every pass on the wavefront kernel under test
             ctx.set_rng(17, 0)
             mp, el, ph, po = make_world(ctx, air_tables, 6000, 0, 800, cap=60000, seed=31)
             P.advance(mp, default_pusher(), 2.5e-11)
