@@ -225,6 +225,12 @@ int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, double L1, 
                                 int32_t nE, int32_t nprocs, const double* rate,
                                 double maxrate, const ptl_process_desc* procs);
 
+/* The same with a VECTOR rate bound on the energy grid (collision_table.jl:35-43):
+ * ratebound(E) = w * v[k] + (1 - w) * v[k + 1] with the (k, w) of the rate lookup; ratebound_vec[nE]. */
+int32_t ptl_table_create_linear_vb(ptl_context* ctx, int32_t grid_kind, double L1, double L2,
+                                   int32_t nE, int32_t nprocs, const double* rate,
+                                   const double* ratebound_vec, const ptl_process_desc* procs);
+
 /* ChebContinuumLoss coefficient matrices (src/continuum.jl:25-43): ec, pc [order, k+1]. */
 int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, double xmax,
                              const double* ec, const double* pc);
@@ -284,6 +290,18 @@ int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, double lo
 int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p);
 /* split!(p, popl) population.jl:316-335 with constant mean number of copies p. */
 int32_t ptl_split(ptl_context* ctx, int32_t pop, double p);
+
+/* roulette!(f, popl) / split!(f, popl) with an energy-dependent law (population.jl:291-309, 316-335).
+ * A closure cannot cross the ABI: the host samples f on `n` nodes, uniform in E [J] (logscale 0) or in
+ * log10(E) (logscale 1) between lo and hi, and the library interpolates linearly (flat outside the
+ * range).  n == 1 is the constant law. */
+int32_t ptl_roulette_law(ptl_context* ctx, int32_t pop, double lo, double hi, int32_t n,
+                         int32_t logscale, const double* p);
+int32_t ptl_split_law(ptl_context* ctx, int32_t pop, double lo, double hi, int32_t n,
+                      int32_t logscale, const double* p);
+/* shuffle!(popl) population.jl:266-271: a uniformly distributed permutation of rows [0, n), drawn
+ * from the counter-based RNG (row index, seed, step) and applied to every column. */
+int32_t ptl_shuffle(ptl_context* ctx, int32_t pop);
 
 /* Raw device pointer of a column for zero-copy interop (NCCL send/recv of column tails,
  * device-side synthetic fills).  col: 0..2 = x0,x1,x2; 3..5 = p0,p1,p2; 6=w 7=t 8=s 9=r

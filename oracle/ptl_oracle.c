@@ -81,6 +81,7 @@ static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 #define DOM_CHILD_UID 0x5EED0001u
 #define DOM_ROULETTE  0x5EED0002u
 #define DOM_SPLIT     0x5EED0003u
+#define DOM_SHUFFLE   0x5EED0004u
 
 typedef struct {
     uint32_t key[2];
@@ -89,6 +90,8 @@ typedef struct {
     uint32_t cblock;    /* block currently cached */
     uint32_t cache[4];
     int have;
+    const double* inject;   /* replay of reference-emitted vectors: the n-th draw is inject[n] (NULL: Philox) */
+    uint32_t ninject;
 } rng_t;
 
 static void rng_init(rng_t* g, uint64_t uid, uint32_t domain, uint64_t seed, uint32_t step) {
@@ -100,6 +103,8 @@ static void rng_init(rng_t* g, uint64_t uid, uint32_t domain, uint64_t seed, uin
     g->idx = 0;
     g->have = 0;
     g->cblock = 0;
+    g->inject = NULL;
+    g->ninject = 0;
 }
 
 /* bits -> double in the open interval (0,1): (m + 0.5) * 2^-52, m = top 52 bits of the 64-bit word
@@ -110,6 +115,11 @@ static inline double bits_to_u01(uint32_t lo, uint32_t hi) {
 }
 
 static double rng_u(rng_t* g) {
+    if (g->inject) {        /* the reference's own rand() sequence, recorded by julia/emit_golden.jl */
+        double u = g->idx < g->ninject ? g->inject[g->idx] : 0.5;
+        g->idx++;
+        return u;
+    }
     uint32_t block = g->idx >> 1;
     if (!g->have || g->cblock != block) {
         uint32_t ctr[4] = {block, g->step, g->seed_lo, g->seed_hi};
@@ -165,6 +175,7 @@ typedef struct {
     /* linear */
     int grid_kind, nE;
     double L1, L2, maxrate;
+    double* rbvec;      /* linear tables: vector rate bound on the energy grid (collision_table.jl:35-43) or NULL */
     double* lrate;     /* [nprocs, nE] */
     int64_t counts[PTL_MAX_PROCS + 1];
 } table_t;
@@ -396,6 +407,13 @@ static double table_ratebound(ora_context* ctx, const table_t* T, double eng) {
         precheb(eng, T->k, T->xmax, T->order, &pre);
         if (pre.oob) FLAG(ctx, PTL_ERR_ENERGY_OUT_OF_TABLE);
         return chebsum(T->ratebound + (size_t)T->order * pre.i, &pre, T->order);
+    }
+    if (T->rbvec) {   /* ratebound(v::Vector, c, eng, pre) collision_table.jl:35-43: the same (k, w) as the rates */
+        pre_t pre;
+        presample(T, eng, &pre);
+        if (pre.oob) FLAG(ctx, PTL_ERR_ENERGY_OUT_OF_TABLE);
+        int k = pre.kidx - 1;
+        return pre.w * T->rbvec[k] + (1 - pre.w) * T->rbvec[k + 1];
     }
     return T->maxrate; /* ratebound(x::Number, ...) collision_table.jl:33 */
 }
@@ -1152,7 +1170,7 @@ EXPORT int32_t ora_context_create(int32_t device, void* stream, ora_context** ou
 
 EXPORT int32_t ora_context_destroy(ora_context* ctx) {
     if (!ctx) return PTL_EINVAL;
-    for (int i = 0; i < ctx->ntab; i++) { free(ctx->tab[i].rate); free(ctx->tab[i].ratebound); free(ctx->tab[i].lrate); }
+    for (int i = 0; i < ctx->ntab; i++) { free(ctx->tab[i].rate); free(ctx->tab[i].ratebound); free(ctx->tab[i].lrate); free(ctx->tab[i].rbvec); }
     for (int i = 0; i < ctx->nsb; i++) { free(ctx->sb[i].log_energy); free(ctx->sb[i].data); }
     for (int i = 0; i < ctx->ncl; i++) { free(ctx->cl[i].ec); free(ctx->cl[i].pc); }
     for (int i = 0; i < ctx->npop; i++) {
@@ -1208,6 +1226,16 @@ EXPORT int32_t ora_table_create_linear(ora_context* ctx, int32_t grid_kind, doub
     T->lrate = dupd(rate, (size_t)nprocs * nE);
     if (nprocs) memcpy(T->procs, procs, sizeof(ptl_process_desc) * nprocs);
     return ctx->ntab++;
+}
+
+EXPORT int32_t ora_table_create_linear_vb(ora_context* ctx, int32_t grid_kind, double L1, double L2, int32_t nE, int32_t nprocs,
+                                          const double* rate, const double* ratebound_vec, const ptl_process_desc* procs) {
+    if (!ratebound_vec) return PTL_EINVAL;
+    double mx = 0;
+    for (int e = 0; e < nE; e++) mx = ratebound_vec[e] > mx ? ratebound_vec[e] : mx;
+    int32_t id = ora_table_create_linear(ctx, grid_kind, L1, L2, nE, nprocs, rate, mx, procs);
+    if (id >= 0) ctx->tab[id].rbvec = dupd(ratebound_vec, (size_t)nE);
+    return id;
 }
 
 EXPORT int32_t ora_cheb_loss_create(ora_context* ctx, int32_t order, int32_t k, double xmax, const double* ec, const double* pc) {
@@ -1395,10 +1423,26 @@ EXPORT int32_t ora_histogram(ora_context* ctx, int32_t pop, int32_t quantity, do
 }
 
 /* roulette!: population.jl:291-309 (constant p) */
-EXPORT int32_t ora_roulette(ora_context* ctx, int32_t pop, double p) {
+/* energy-dependent law of roulette!(f, popl) / split!(f, popl): f tabulated on n nodes uniform in E or log10(E) between lo and hi,
+ * linear interpolation, flat outside (n == 1: constant) */
+static double law_value(double eng, double lo, double hi, int32_t n, int32_t logscale, const double* v) {
+    if (n <= 1) return v[0];
+    double x = logscale ? log10(eng) : eng;
+    double u = (x - lo) / (hi - lo) * (double)(n - 1);
+    if (!(u > 0)) return v[0];
+    if (u >= (double)(n - 1)) return v[n - 1];
+    int k = (int)u;
+    double f = u - (double)k;
+    return v[k] * (1 - f) + v[k + 1] * f;
+}
+
+/* roulette!(f, popl): population.jl:291-309 */
+EXPORT int32_t ora_roulette_law(ora_context* ctx, int32_t pop, double lo, double hi, int32_t n, int32_t logscale, const double* pv) {
     GETPOP(ctx, pop, PTL_EHANDLE);
+    if (n < 1 || !pv || (n > 1 && !(hi > lo))) return PTL_EINVAL;
     for (int64_t i = 0; i < P->n; i++) {
         if (!P->active[i]) continue;
+        double p = law_value(kinenergy(P->species, load_state(P, i).p), lo, hi, n, logscale, pv);
         rng_t g;
         rng_init(&g, P->uid[i], DOM_ROULETTE, ctx->seed, ctx->step);
         if (rng_u(&g) < p) P->w[i] /= p;
@@ -1407,14 +1451,17 @@ EXPORT int32_t ora_roulette(ora_context* ctx, int32_t pop, double p) {
     ctx->step++;
     return 0;
 }
+EXPORT int32_t ora_roulette(ora_context* ctx, int32_t pop, double p) { return ora_roulette_law(ctx, pop, 0, 1, 1, 0, &p); }
 
-/* split!: population.jl:316-335 (constant p); Poisson(p) by sequential inversion; copies get
+/* split!(f, popl): population.jl:316-335; Poisson(p) by sequential inversion; copies get
  * fresh uids so that their streams differ (the reference relies on a shared global RNG) */
-EXPORT int32_t ora_split(ora_context* ctx, int32_t pop, double p) {
+EXPORT int32_t ora_split_law(ora_context* ctx, int32_t pop, double lo, double hi, int32_t n, int32_t logscale, const double* pv) {
     GETPOP(ctx, pop, PTL_EHANDLE);
+    if (n < 1 || !pv || (n > 1 && !(hi > lo))) return PTL_EINVAL;
     int64_t n0 = P->n;
     for (int64_t i = 0; i < n0; i++) {
         if (!P->active[i]) continue;
+        double p = law_value(kinenergy(P->species, load_state(P, i).p), lo, hi, n, logscale, pv);
         P->w[i] /= (1 + p);
         rng_t g;
         rng_init(&g, P->uid[i], DOM_SPLIT, ctx->seed, ctx->step);
@@ -1428,6 +1475,39 @@ EXPORT int32_t ora_split(ora_context* ctx, int32_t pop, double p) {
             child_uids(P->uid[i] ^ ((uint64_t)DOM_SPLIT << 32), (uint32_t)c, ctx->seed, ctx->step, cu);
             add_particle(ctx, P, &st, cu[0]);
         }
+    }
+    ctx->step++;
+    return ctx->flags;
+}
+EXPORT int32_t ora_split(ora_context* ctx, int32_t pop, double p) { return ora_split_law(ctx, pop, 0, 1, 1, 0, &p); }
+
+/* shuffle!(popl): population.jl:266-271, a uniformly distributed permutation of the rows.  The reference runs Fisher-Yates
+ * on the global RNG; here every row draws a 64-bit key from the Philox stream of (row index, seed, step) and the rows are
+ * sorted by key (ties by row index): also uniform over permutations, and reproducible on any number of threads. */
+typedef struct { uint64_t key; int64_t row; } shuf_t;
+static int shuf_cmp(const void* a, const void* b) {
+    const shuf_t *x = a, *y = b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->row < y->row ? -1 : (x->row > y->row);
+}
+EXPORT int32_t ora_shuffle(ora_context* ctx, int32_t pop) {
+    GETPOP(ctx, pop, PTL_EHANDLE);
+    int64_t n = P->n;
+    if (n > 1) {
+        shuf_t* k = malloc(sizeof(shuf_t) * (size_t)n);
+        for (int64_t i = 0; i < n; i++) {
+            uint32_t key[2] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32) ^ DOM_SHUFFLE};
+            uint32_t ctr[4] = {0, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)}, o[4];
+            philox4x32_10(ctr, key, o);
+            k[i].key = ((uint64_t)o[1] << 32) | o[0];
+            k[i].row = i;
+        }
+        qsort(k, (size_t)n, sizeof(shuf_t), shuf_cmp);
+        state_t* tmp = malloc(sizeof(state_t) * (size_t)n);
+        uint64_t* tu = malloc(sizeof(uint64_t) * (size_t)n);
+        for (int64_t i = 0; i < n; i++) { tmp[i] = load_state(P, k[i].row); tu[i] = P->uid[k[i].row]; }
+        for (int64_t i = 0; i < n; i++) { store_state(P, i, &tmp[i]); P->uid[i] = tu[i]; }
+        free(tmp); free(tu); free(k);
     }
     ctx->step++;
     return 0;
@@ -1518,6 +1598,36 @@ EXPORT int32_t ora_collide_test(ora_context* ctx, int32_t species, int32_t table
     for (int64_t i = 0; i < n; i++) {
         rng_t g;
         rng_init(&g, uid0 + (uint64_t)i, DOM_COLLISION, ctx->seed, ctx->step);
+        state_t st;
+        memset(&st, 0, sizeof(st));
+        for (int c = 0; c < 3; c++) st.p.v[c] = p3[3 * i + c];
+        st.w = 1.0; st.active = 1;
+        outcome_t o;
+        memset(&o, 0, sizeof(o));
+        collide(ctx, &g, &T->procs[j], species, &st, kinenergy(species, st.p), &o);
+        double* r = out + 24 * i;
+        memset(r, 0, sizeof(double) * 24);
+        r[0] = o.kind; r[1] = o.sp2; r[2] = o.sp3; r[3] = g.idx;
+        if (o.kind == OUT_STATE_CHANGE || o.kind == OUT_NEW_PARTICLE) { for (int c = 0; c < 3; c++) r[4 + c] = o.s1.p.v[c]; r[7] = o.s1.s; }
+        if (o.kind == OUT_NEW_PARTICLE || o.kind == OUT_REPLACE || o.kind == OUT_REPLACE_PAIR) { for (int c = 0; c < 3; c++) r[8 + c] = o.s2.p.v[c]; r[11] = o.s2.s; }
+        if (o.kind == OUT_REPLACE_PAIR) { for (int c = 0; c < 3; c++) r[12 + c] = o.s3.p.v[c]; r[15] = o.s3.s; }
+    }
+    return 0;
+}
+
+/* Replay of REFERENCE-emitted vectors (julia/emit_golden.jl -> tests/golden/reference_vectors.npz): collide() of process j with
+ * the reference's own rand() sequence injected draw by draw (uniforms[nu] per event).  Same output layout as ora_collide_test;
+ * out[3] = draws consumed.  This is what pins the samplers against the reference itself once a Julia runtime is available. */
+EXPORT int32_t ora_collide_replay(ora_context* ctx, int32_t species, int32_t table, int32_t j, int64_t n, const double* p3,
+                                  const double* uniforms, int32_t nu, double* out) {
+    if (table < 0 || table >= ctx->ntab) return PTL_EHANDLE;
+    const table_t* T = &ctx->tab[table];
+    if (j < 0 || j >= T->nprocs || nu < 1 || !uniforms) return PTL_EINVAL;
+    for (int64_t i = 0; i < n; i++) {
+        rng_t g;
+        rng_init(&g, 1, DOM_COLLISION, 0, 0);
+        g.inject = uniforms + (size_t)nu * i;
+        g.ninject = (uint32_t)nu;
         state_t st;
         memset(&st, 0, sizeof(st));
         for (int c = 0; c < 3; c++) st.p.v[c] = p3[3 * i + c];

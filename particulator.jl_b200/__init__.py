@@ -24,7 +24,7 @@ from .pusher import (NullForcing, CombinedForcing, RestrictedForcing, RK2Pusher,
                      ContinuumLoss, ChebContinuumLoss)
 from .population import (Population, kinenergy, momentum_norm_from_kin, nparticles, nactives, weight, meanenergy,
                          maxenergy, spread, posvar, empty, add_particle, remove_particle, repack, droplow, roulette,
-                         split)
+                         split, shuffle)
 from .mixed_population import MultiPopulation, init, advance, last_advance_stats
 from .callback import (AbstractCallback, VoidCallback, CombinedCallback, CollisionCounter, WallCallback,
                        ParticleCountCallback, RouletteCallback, SplitCallback, PopulationTargetCallback)

@@ -104,6 +104,11 @@ _SIGS = {
     "wall_records": (C.c_int64, [_vp, C.c_int32, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32]),
     "collide_test": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, C.c_uint64, _dp]),
     "rng_test": (C.c_int32, [_vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int32, _dp]),
+    "table_create_linear_vb": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp, _dp,
+                                           C.POINTER(ProcessDesc)]),
+    "roulette_law": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp]),
+    "split_law": (C.c_int32, [_vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, _dp]),
+    "shuffle": (C.c_int32, [_vp, C.c_int32]),
     "set_uid_counter": (C.c_int32, [_vp, C.c_uint64]),
     "get_uid_counter": (C.c_uint64, [_vp]),
 }

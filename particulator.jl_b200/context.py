@@ -119,9 +119,15 @@ class Context:
                                                 rb.ctypes.data_as(C.POINTER(C.c_double)), procs)
         elif isinstance(tab, CollisionTable):
             rate = np.asfortranarray(tab.rate)          # [nprocs, nE], process fastest
-            rc = self.backend.table_create_linear(self.h, tab.grid_kind, float(tab.L1), float(tab.L2), tab.nE,
-                                                  len(tab.proc), rate.ctypes.data_as(C.POINTER(C.c_double)),
-                                                  float(tab.maxrate), procs)
+            if tab.ratebound is not None:               # vector rate bound (collision_table.jl:35-43)
+                rb = as_f64(tab.ratebound).ravel()
+                assert len(rb) == tab.nE
+                rc = self.backend.table_create_linear_vb(self.h, tab.grid_kind, float(tab.L1), float(tab.L2), tab.nE,
+                                                         len(tab.proc), rate.ctypes.data_as(C.POINTER(C.c_double)), dptr(rb), procs)
+            else:
+                rc = self.backend.table_create_linear(self.h, tab.grid_kind, float(tab.L1), float(tab.L2), tab.nE,
+                                                      len(tab.proc), rate.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      float(tab.maxrate), procs)
         else:
             raise TypeError(type(tab))
         tid = self.check(rc, "table_create")

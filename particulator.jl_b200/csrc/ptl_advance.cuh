@@ -60,7 +60,7 @@ __device__ __forceinline__ double own_ratebound(const AdvanceParams& P, const Sm
         if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
         return chebsum(S.ratebound + T.order * pre.i, pre, T.order);
     }
-    return T.maxrate;
+    return ratebound_global(T, eng, P.flags);
 }
 
 // setr!: collisions.jl:63-74

@@ -436,7 +436,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
                 int kind = jsel >= 0 ? TS.procs[jsel].kind : PTL_PROC_NULL;
                 if (kind == PTL_PROC_NULL) {            // NullOutcome: setr! then s = nextcoll()  (:83-88, :182-196)
                     // setr! recomputes kinenergy and presample from the same p: reuse them
-                    r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : T.maxrate;
+                    r = (TK == 0) ? chebsum(TS.ratebound + T.order * pre.i, pre, T.order) : (T.rbvec != nullptr ? linear_bound(T, pre) : T.maxrate);
                     if (CB) {
                         s = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
                     } else {

@@ -2,6 +2,8 @@
 // upload, and the host-side launch logic of every kernel (advance pass loop, compaction, diagnostics).
 // Plain C signatures only; no torch / C++ types cross the boundary.  There is NO CPU fallback: a
 // context can only be created on a compute-capability-10.x device.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "ptl_host.h"
 #include "ptl_advance.cuh"
 #include "ptl_store.cuh"
@@ -89,7 +91,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     if (!ctx) return PTL_EINVAL;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_cum); cudaFree(t.d_cum2); cudaFree(t.d_procs); cudaFree(t.d_counts); }
+    for (auto& t : ctx->tables) { cudaFree(t.d_rate); cudaFree(t.d_rb); cudaFree(t.d_cum); cudaFree(t.d_cum2); cudaFree(t.d_rbvec); cudaFree(t.d_procs); cudaFree(t.d_counts); }
     for (auto& p : ctx->pops) if (p.block) cudaFree(p.block);
     for (auto& s : ctx->sbs) { cudaFree((void*)s.v.log_energy); cudaFree((void*)s.v.data); }
     for (auto& c : ctx->cls) { cudaFree((void*)c.v.ec); cudaFree((void*)c.v.pc); }
@@ -293,6 +295,20 @@ EXPORT int32_t ptl_table_create_linear(ptl_context* ctx, int32_t grid_kind, doub
     T.smem_bytes = sizeof(ptl_process_desc) * nprocs;
     ctx->tables.push_back(T);
     return (int32_t)ctx->tables.size() - 1;
+}
+
+EXPORT int32_t ptl_table_create_linear_vb(ptl_context* ctx, int32_t grid_kind, double L1, double L2, int32_t nE, int32_t nprocs,
+                                          const double* rate, const double* ratebound_vec, const ptl_process_desc* procs) {
+    PTL_BIND(ctx);
+    if (!ctx || !ratebound_vec || nE < 2) return PTL_EINVAL;
+    double mx = 0;
+    for (int e = 0; e < nE; e++) mx = ratebound_vec[e] > mx ? ratebound_vec[e] : mx;
+    int32_t id = ptl_table_create_linear(ctx, grid_kind, L1, L2, nE, nprocs, rate, mx, procs);
+    if (id < 0) return id;
+    Table& T = ctx->tables[id];
+    int32_t rc = upload_doubles(ctx, ratebound_vec, (size_t)nE, &T.d_rbvec); if (rc) return rc;
+    T.v.rbvec = T.d_rbvec;
+    return id;
 }
 
 EXPORT int32_t ptl_cheb_loss_create(ptl_context* ctx, int32_t order, int32_t k, double xmax, const double* ec, const double* pc) {
@@ -660,33 +676,101 @@ EXPORT int32_t ptl_histogram(ptl_context* ctx, int32_t pop, int32_t quantity, do
     return 0;
 }
 
-EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
+namespace {
+// stage the nodes of an energy law on the device (n == 1: the constant travels in the struct)
+int32_t make_law(ptl_context* ctx, double lo, double hi, int32_t n, int32_t logscale, const double* v, EnergyLaw* L) {
+    if (n < 1 || n > (1 << 20) || !v || (n > 1 && !(hi > lo))) return PTL_EINVAL;
+    L->lo = lo; L->hi = hi; L->n = n; L->logscale = logscale; L->c = v[0]; L->v = nullptr;
+    if (n > 1) {
+        int32_t rc = ensure_tmp(ctx, sizeof(double) * (size_t)n); if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_tmp, v, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));      // the host array is only borrowed
+        L->v = (const double*)ctx->d_tmp;
+    }
+    return 0;
+}
+}  // namespace
+
+EXPORT int32_t ptl_roulette_law(ptl_context* ctx, int32_t pop, double lo, double hi, int32_t nn, int32_t logscale, const double* pv) {
     PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
-    if (!P || !(p > 0)) return PTL_EINVAL;
+    if (!P) return PTL_EHANDLE;
+    EnergyLaw L;
+    int32_t rc = make_law(ctx, lo, hi, nn, logscale, pv, &L); if (rc) return rc;
     long long n = 0;
-    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    rc = read_n(ctx, *P, &n); if (rc) return rc;
     if (n > 0) {
-        k_roulette<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32));
+        k_roulette<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, L, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32));
         LAUNCHED();
     }
     ctx->step++;
     return 0;
 }
 
-EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
+EXPORT int32_t ptl_roulette(ptl_context* ctx, int32_t pop, double p) {
+    if (!(p > 0)) return PTL_EINVAL;
+    return ptl_roulette_law(ctx, pop, 0.0, 1.0, 1, 0, &p);
+}
+
+EXPORT int32_t ptl_split_law(ptl_context* ctx, int32_t pop, double lo, double hi, int32_t nn, int32_t logscale, const double* pv) {
     PTL_BIND(ctx);
     Pop* P = get_pop(ctx, pop);
-    if (!P || !(p >= 0)) return PTL_EINVAL;
+    if (!P) return PTL_EHANDLE;
+    EnergyLaw L;
+    int32_t rc = make_law(ctx, lo, hi, nn, logscale, pv, &L); if (rc) return rc;
     long long n = 0;
-    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    rc = read_n(ctx, *P, &n); if (rc) return rc;
     if (n > 0) {
-        k_split<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, p, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), &ctx->d_sc->flags);
+        k_split<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v, n, L, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32), &ctx->d_sc->flags);
         LAUNCHED();
     }
     ctx->step++;
     rc = read_n(ctx, *P, &n); if (rc) return rc;
     return ctx->h_sc->flags;
+}
+
+EXPORT int32_t ptl_split(ptl_context* ctx, int32_t pop, double p) {
+    if (!(p >= 0)) return PTL_EINVAL;
+    return ptl_split_law(ctx, pop, 0.0, 1.0, 1, 0, &p);
+}
+
+// shuffle!(popl) population.jl:266-271
+EXPORT int32_t ptl_shuffle(ptl_context* ctx, int32_t pop) {
+    PTL_BIND(ctx);
+    Pop* P = get_pop(ctx, pop);
+    if (!P) return PTL_EHANDLE;
+    long long n = 0;
+    int32_t rc = read_n(ctx, *P, &n); if (rc) return rc;
+    if (n > 1) {
+        size_t sort_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (long long*)nullptr,
+                                        (long long*)nullptr, (int)n, 0, 64, ctx->stream);
+        const size_t nb = align256(sizeof(unsigned long long) * (size_t)n);
+        rc = ensure_tmp(ctx, 5 * nb + align256(sort_bytes)); if (rc) return rc;
+        char* base = (char*)ctx->d_tmp;
+        unsigned long long *k0 = (unsigned long long*)base, *k1 = (unsigned long long*)(base + nb);
+        long long *r0 = (long long*)(base + 2 * nb), *r1 = (long long*)(base + 3 * nb);
+        double* col = (double*)(base + 4 * nb);
+        void* sort_tmp = base + 5 * nb;
+        k_shuffle_keys<<<grid_for(n, 256), 256, 0, ctx->stream>>>(k0, r0, n, ctx->step, (uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32));
+        LAUNCHED();
+        // stable LSD radix sort: equal keys keep their row order, like the oracle's (key, row) comparison
+        CK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k0, k1, r0, r1, (int)n, 0, 64, ctx->stream));
+        ctx->launch_total++;
+        for (int c = 0; c < 10; c++) {
+            k_gather<double><<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.col[c], r1, col, n);
+            LAUNCHED();
+            CK(cudaMemcpyAsync(P->v.col[c], col, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        k_gather<uint64_t><<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.uid, r1, (uint64_t*)col, n);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(P->v.uid, col, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        k_gather<uint8_t><<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.active, r1, (uint8_t*)col, n);
+        LAUNCHED();
+        CK(cudaMemcpyAsync(P->v.active, col, (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->step++;
+    return 0;
 }
 
 // =====================================================================================================

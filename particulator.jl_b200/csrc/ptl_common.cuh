@@ -59,6 +59,7 @@ struct TableView {
     const double2* cum2;             // linear tables: {cum[j, e], cum[j, e + 1]} per (j, e): one 16-byte load per search probe
     int grid_kind, nE;
     double L1, L2, maxrate;
+    const double* rbvec;             // linear tables: vector rate bound on the energy grid (collision_table.jl:35-43) or nullptr
     const ptl_process_desc* procs;   // device copy
     unsigned long long* counts;      // [nprocs + 1]
     unsigned long long mono_mask;    // cheb, order 3: bit i set <=> every fitted rate is >= 0 on interval i, so the running
@@ -127,6 +128,7 @@ constexpr uint32_t DOM_COLLISION = 0u;
 constexpr uint32_t DOM_CHILD_UID = 0x5EED0001u;
 constexpr uint32_t DOM_ROULETTE = 0x5EED0002u;
 constexpr uint32_t DOM_SPLIT = 0x5EED0003u;
+constexpr uint32_t DOM_SHUFFLE = 0x5EED0004u;
 
 // 64 random bits -> double in the OPEN interval (0,1): (m + 0.5) * 2^-52 with m the top 52 bits.
 // Built as [1,2) mantissa + one exact add (no int->double conversion).

@@ -32,7 +32,7 @@ struct DeviceScalars {            // one small device block mirrored in pinned h
 struct Table {
     TableView v{};
     std::vector<ptl_process_desc> procs;
-    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr, *d_cum2 = nullptr;
+    double *d_rate = nullptr, *d_rb = nullptr, *d_cum = nullptr, *d_cum2 = nullptr, *d_rbvec = nullptr;
     ptl_process_desc* d_procs = nullptr;
     unsigned long long* d_counts = nullptr;
     size_t smem_bytes = 0;

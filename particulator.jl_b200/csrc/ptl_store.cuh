@@ -241,22 +241,45 @@ __global__ void k_histogram(PopView Q, long long n, int quantity, double lo, dou
     for (int b = threadIdx.x; b < nbins; b += blockDim.x) if (bins[b] != 0) atomicAdd(&out[b], bins[b]);
 }
 
-// ---- K4: roulette! (population.jl:291-309) and split! (:316-335) with constant p ---------------------------------
-__global__ void k_roulette(PopView Q, long long n, double prob, uint32_t step, uint32_t seed_lo, uint32_t seed_hi) {
+// ---- K4: roulette! (population.jl:291-309) and split! (:316-335) ------------------------------------------------------
+// f(energy) of roulette!(f, popl) / split!(f, popl): tabulated by the host on n nodes uniform in E or log10(E) between lo
+// and hi, interpolated linearly, flat outside; n == 1 is the constant law (the value travels in `c`).
+struct EnergyLaw {
+    double lo, hi, c;
+    int n, logscale;
+    const double* v;
+};
+__device__ __forceinline__ double law_value(const EnergyLaw& L, double eng) {
+    if (L.n <= 1) return L.c;
+    double x = L.logscale ? log10(eng) : eng;
+    double u = (x - L.lo) / (L.hi - L.lo) * (double)(L.n - 1);
+    if (!(u > 0)) return L.v[0];
+    if (u >= (double)(L.n - 1)) return L.v[L.n - 1];
+    int k = (int)u;
+    double f = u - (double)k;
+    return L.v[k] * (1 - f) + L.v[k + 1] * f;
+}
+
+static __global__ void k_roulette(PopView Q, long long n, EnergyLaw L, uint32_t step, uint32_t seed_lo, uint32_t seed_hi) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n || !Q.active[i]) return;
+    Vec3 pp = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+    const double prob = law_value(L, kinenergy_rt(Q.species, pp));
     Rng rng;
     rng.init(Q.uid[i], DOM_ROULETTE);
     if (rng.u(step, seed_lo, seed_hi) < prob) Q.col[COL_W][i] /= prob;
     else Q.active[i] = 0;
 }
 
-__global__ void k_split(PopView Q, long long n, double pmean, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, int* flags) {
+static __global__ void k_split(PopView Q, long long n, EnergyLaw L, uint32_t step, uint32_t seed_lo, uint32_t seed_hi, int* flags) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int k = 0;
     bool act = i < n && Q.active[i];
     double w = 0;
     if (act) {
+        Vec3 pp = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
+        const double eng = kinenergy_rt(Q.species, pp);
+        const double pmean = law_value(L, eng);
         w = Q.col[COL_W][i] / (1 + pmean);
         Q.col[COL_W][i] = w;
         Rng rng;
@@ -264,8 +287,7 @@ __global__ void k_split(PopView Q, long long n, double pmean, uint32_t step, uin
         double u = rng.u(step, seed_lo, seed_hi);
         double pk = exp(-pmean), cdf = pk;   // Poisson(p) by sequential inversion
         while (u > cdf && k < 1000) { k++; pk *= pmean / k; cdf += pk; }
-        Vec3 pp = {Q.col[COL_P0][i], Q.col[COL_P1][i], Q.col[COL_P2][i]};
-        if (!(kinenergy_rt(Q.species, pp) > Q.energy_cut)) k = 0;   // add_particle! refuses copies at or below the cut (population.jl:105)
+        if (!(eng > Q.energy_cut)) k = 0;   // add_particle! refuses copies at or below the cut (population.jl:105)
     }
     // warp-aggregated append of all copies
     int lane = threadIdx.x & 31;
@@ -290,6 +312,22 @@ __global__ void k_split(PopView Q, long long n, double pmean, uint32_t step, uin
         Q.active[slot] = 1;
         Q.uid[slot] = cu[0];
     }
+}
+
+// ---- shuffle! (population.jl:266-271): sort the rows by a 64-bit key drawn from the counter-based RNG -----------------
+static __global__ void k_shuffle_keys(unsigned long long* __restrict__ keys, long long* __restrict__ rowid, long long n, uint32_t step,
+                                      uint32_t seed_lo, uint32_t seed_hi) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    philox4x32_10(0u, step, seed_lo, seed_hi, (uint32_t)i, (uint32_t)((unsigned long long)i >> 32) ^ DOM_SHUFFLE, o);
+    keys[i] = ((unsigned long long)o[1] << 32) | o[0];
+    rowid[i] = i;
+}
+template <typename T>
+static __global__ void k_gather(const T* __restrict__ src, const long long* __restrict__ idx, T* __restrict__ dst, long long n) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
 }
 
 }  // namespace ptl

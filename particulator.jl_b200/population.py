@@ -182,9 +182,40 @@ def droplow(popl, thres=0.0):
     return int(popl.ctx.check(int(popl.ctx.backend.droplow(popl.ctx.h, popl.id, float(thres))), "droplow"))
 
 
-def roulette(p, popl):
-    popl.ctx.raise_on_flags(popl.ctx.backend.roulette(popl.ctx.h, popl.id, float(p)), "roulette")
+def _law_nodes(f, lo, hi, nodes, logscale):
+    """Sample a Python callable f(energy [J]) on the nodes the library interpolates between."""
+    x = np.linspace(math.log10(lo) if logscale else lo, math.log10(hi) if logscale else hi, nodes)
+    e = 10.0 ** x if logscale else x
+    v = np.ascontiguousarray([float(f(float(q))) for q in e], dtype=np.float64)
+    return float(x[0]), float(x[-1]), v
 
 
-def split(p, popl):
-    popl.ctx.raise_on_flags(popl.ctx.backend.split(popl.ctx.h, popl.id, float(p)), "split")
+def roulette(p, popl, lo=None, hi=None, nodes=1024, logscale=True):
+    """roulette!(f_or_p, popl) (population.jl:291-314).  A number is the constant retain probability; a callable f(energy)
+    is sampled on `nodes` nodes between `lo` and `hi` (default: energy_cut .. 1 GeV, log-spaced) and interpolated linearly
+    on the device — a closure cannot cross the C ABI."""
+    if callable(p):
+        lo = lo if lo is not None else max(popl.energy_cut, 1e-3 * co.eV)
+        hi = hi if hi is not None else 1e9 * co.eV
+        x0, x1, v = _law_nodes(p, lo, hi, nodes, logscale)
+        rc = popl.ctx.backend.roulette_law(popl.ctx.h, popl.id, x0, x1, len(v), 1 if logscale else 0, dptr(v))
+    else:
+        rc = popl.ctx.backend.roulette(popl.ctx.h, popl.id, float(p))
+    popl.ctx.raise_on_flags(rc, "roulette")
+
+
+def split(p, popl, lo=None, hi=None, nodes=1024, logscale=True):
+    """split!(f_or_p, popl) (population.jl:316-340): mean number of copies, constant or a callable of the energy."""
+    if callable(p):
+        lo = lo if lo is not None else max(popl.energy_cut, 1e-3 * co.eV)
+        hi = hi if hi is not None else 1e9 * co.eV
+        x0, x1, v = _law_nodes(p, lo, hi, nodes, logscale)
+        rc = popl.ctx.backend.split_law(popl.ctx.h, popl.id, x0, x1, len(v), 1 if logscale else 0, dptr(v))
+    else:
+        rc = popl.ctx.backend.split(popl.ctx.h, popl.id, float(p))
+    popl.ctx.raise_on_flags(rc, "split")
+
+
+def shuffle(popl):
+    """shuffle!(popl) (population.jl:266-271): a uniformly distributed permutation of the rows."""
+    popl.ctx.check(popl.ctx.backend.shuffle(popl.ctx.h, popl.id), "shuffle")

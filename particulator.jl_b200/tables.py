@@ -36,7 +36,8 @@ class ChebyshevCollisionTable:
 @dataclass
 class CollisionTable:
     """collision_table.jl:15-28 with a LinRange (grid_kind 0) or LogLinRange (grid_kind 1) energy grid
-    and a constant rate bound (`maxrate`, collision_table.jl:33)."""
+    and a constant rate bound (`maxrate`, collision_table.jl:33) or a vector rate bound on the energy grid
+    (`ratebound`, collision_table.jl:35-43)."""
     proc: list
     grid_kind: int
     L1: float
@@ -45,6 +46,7 @@ class CollisionTable:
     rate: np.ndarray        # [nprocs, nE]
     maxrate: float
     species: int = SLOW_ELECTRON
+    ratebound: np.ndarray = None   # [nE] or None
 
     def __len__(self):
         return len(self.proc)

@@ -6,6 +6,9 @@ Tiers:
     rel 1e-6 in fp64 (tolerance written below as REPLAY_RTOL);
   * properties at larger sizes that do not need the oracle.
 Run on a B200 with:  python -m pytest tests -m gpu -x -q"""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -180,13 +183,39 @@ def _by_uid(pop):
     return {k: v[order] for k, v in d.items()}
 
 
-def _compare_populations(gp, op, label, budget=0.002):
+#: observed per-test mismatch counts (label -> (mismatching particles, particles compared)); written to
+#: gpurun_out/replay_mismatches.json at the end of the session and asserted to be zero test by test
+OBSERVED_MISMATCHES = {}
+#: PTL_REPLAY_BUDGET=<fraction> relaxes the zero-mismatch assertion (the count is still printed and recorded)
+_BUDGET_OVERRIDE = float(os.environ.get("PTL_REPLAY_BUDGET", "0"))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _record_mismatches():
+    yield
+    if OBSERVED_MISMATCHES:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        try:
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "replay_mismatches.json"), "w") as f:
+                json.dump({"total_mismatches": sum(v[0] for v in OBSERVED_MISMATCHES.values()),
+                           "total_compared": sum(v[1] for v in OBSERVED_MISMATCHES.values()), "by_test": OBSERVED_MISMATCHES}, f, indent=1)
+        except OSError:
+            pass
+
+
+def _compare_populations(gp, op, label, budget=0.0):
+    """Per-particle comparison matched by uid.  A mismatching particle is one whose trajectory took a different branch at a
+    compare within rounding of its threshold.  Round 1 allowed 0.2 % of them silently; the observed count has always been 0,
+    so it is now ASSERTED to be zero (budget = 0), printed, and recorded."""
+    budget = max(budget, _BUDGET_OVERRIDE)
     g, o = _by_uid(gp), _by_uid(op)
     ug, uo = g["uid"], o["uid"]
     common, ig, io = np.intersect1d(ug, uo, return_indices=True)
     nmiss = (len(ug) - len(common)) + (len(uo) - len(common))
-    assert nmiss <= max(2, budget * max(len(ug), 1)), (label, len(ug), len(uo), len(common))
+    assert nmiss <= budget * max(len(ug), 1), (label, "uids present on one side only", nmiss, len(ug), len(uo), len(common))
     if len(common) == 0:
+        OBSERVED_MISMATCHES[label] = (nmiss, 0)
         return 0
     pscale = np.maximum(np.linalg.norm(o["p"][io], axis=1), 1e-300)[:, None]
     bad = (np.abs(g["p"][ig] - o["p"][io]) / pscale).max(axis=1) > REPLAY_RTOL
@@ -196,10 +225,11 @@ def _compare_populations(gp, op, label, budget=0.002):
     bad |= np.abs(g["r"][ig] - o["r"][io]) > REPLAY_RTOL * np.maximum(np.abs(o["r"][io]), 1.0)
     bad |= g["active"][ig] != o["active"][io]
     bad |= g["w"][ig] != o["w"][io]
-    # a mismatching particle is one whose trajectory took a different branch at a compare within rounding of its
-    # threshold; the budget is deliberately tiny and the count is reported
-    assert bad.sum() <= max(2, budget * len(common)), (label, int(bad.sum()), len(common))
-    return int(bad.sum()) + nmiss
+    nbad = int(bad.sum()) + nmiss
+    OBSERVED_MISMATCHES[label] = (nbad, int(len(common)))
+    print(f"[replay] {label}: {nbad} mismatching of {len(common)} particles compared")
+    assert bad.sum() <= budget * len(common), (label, "mismatching particles", int(bad.sum()), len(common))
+    return nbad
 
 
 @pytest.mark.parametrize("seed,n_e,n_g,n_p", [(0, 3000, 3000, 1000), (1, 257, 0, 0), (2, 0, 5000, 0), (3, 0, 0, 777)])
@@ -610,3 +640,246 @@ def test_lepton_kernel_variants_are_bit_identical(gctx, air_tables, variant):
         assert np.array_equal(ref[nm]["uid"], got[nm]["uid"]), nm
         for k in ("x", "p", "t", "s", "r", "w", "active"):
             assert np.array_equal(ref[nm][k].view(np.uint8), got[nm][k].view(np.uint8)), (nm, k)
+
+
+# ---------------------------------------------------------------------------------------------------
+# API completeness (round 2): energy-dependent roulette!/split!, shuffle!, vector rate bound
+# ---------------------------------------------------------------------------------------------------
+def _retain_law(eng):
+    """Retain probability falling with energy: keep every MeV electron, 20 % of the keV ones."""
+    return float(np.clip(0.2 + 0.8 * (np.log10(eng / co.eV) - 3.0) / 3.0, 0.2, 1.0))
+
+
+@pytest.mark.gpu
+def test_energy_dependent_roulette_and_split_replay(gctx, octx, air_tables):
+    """roulette!(f, popl) / split!(f, popl) with f a function of the energy (population.jl:291-309, 316-335): the law is
+    tabulated by the host; the CUDA path and the oracle make the same per-particle decisions (same uid-keyed draws)."""
+    st = _random_pop(np.random.default_rng(5), 40000, 0.05)
+    out = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(3, 9)
+        pop = P.Population(ctx, P.ELECTRON, 200000, st, air_tables["electron"], 1e3 * co.eV)
+        P.roulette(_retain_law, pop, lo=1e3 * co.eV, hi=1e7 * co.eV, nodes=257)
+        a = pop.download()
+        P.repack(pop)
+        P.split(lambda e: 2.0 if e > 1e6 * co.eV else 0.25, pop, lo=1e3 * co.eV, hi=1e7 * co.eV, nodes=513)
+        b = pop.download()
+        out.append((a, b))
+    (ag, bg), (ao, bo) = out
+    assert np.array_equal(ag["active"], ao["active"])
+    np.testing.assert_allclose(ag["w"], ao["w"], rtol=1e-12)
+    eng = P.kinenergy(P.ELECTRON, st["p"])
+    alive0 = st["active"] == 1
+    for lo_e, hi_e, expect in [(1e3, 3e3, 0.26), (1e6, 1e7, 1.0)]:
+        m = alive0 & (eng > lo_e * co.eV) & (eng < hi_e * co.eV)
+        kept = ag["active"][m].mean()
+        assert abs(kept - expect) < 0.05, (lo_e, kept)
+    assert sorted(bg["uid"].tolist()) == sorted(bo["uid"].tolist())
+    assert len(bg["uid"]) > int(ag["active"].sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 1000, 100003])
+def test_shuffle_same_permutation(gctx, octx, air_tables, n):
+    """shuffle!(popl) (population.jl:266-271): the CUDA path and the oracle apply the SAME permutation (keys from the
+    counter-based RNG), every column moves with its row, and the permutation changes from call to call."""
+    st = _random_pop(np.random.default_rng(n), n, 0.2)
+    res = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(99, 4)
+        pop = P.Population(ctx, P.ELECTRON, n + 8, st, air_tables["electron"], 1e3 * co.eV)
+        P.shuffle(pop)
+        first = pop.download()
+        P.shuffle(pop)
+        res.append((first, pop.download()))
+    (g1, g2), (o1, o2) = res
+    for k in g1:
+        assert np.array_equal(g1[k], o1[k]), k
+        assert np.array_equal(g2[k], o2[k]), k
+    assert sorted(g1["uid"].tolist()) == sorted(st["uid"].tolist())
+    src = {u: i for i, u in enumerate(st["uid"].tolist())}
+    perm = np.array([src[u] for u in g1["uid"].tolist()])
+    assert np.array_equal(g1["p"], st["p"][perm]) and np.array_equal(g1["active"], st["active"][perm])
+    if n > 100:
+        assert (perm != np.arange(n)).mean() > 0.9 and not np.array_equal(g1["uid"], g2["uid"])
+
+
+def _vb_table():
+    """Linear (LXCat-style) table whose rate bound is a VECTOR on the energy grid (collision_table.jl:35-43)."""
+    lin = P.synthetic_lxcat_table(grid_kind=0, nE=512)
+    tot = lin.rate.sum(axis=0)                       # includes the explicit null row: constant = maxrate
+    real = tot - lin.rate[[i for i, p in enumerate(lin.proc) if type(p).__name__ == "NullCollision"][0]]
+    # a bound that hugs the real total rate (x1.2, running maximum over neighbours) instead of the global maximum
+    rb = 1.2 * np.maximum.reduce([np.roll(real, k) for k in (-2, -1, 0, 1, 2)])
+    rb[:2] = rb[2]; rb[-2:] = rb[-3]
+    procs = [p for p in lin.proc if type(p).__name__ != "NullCollision"]
+    rate = np.ascontiguousarray(lin.rate[[i for i, p in enumerate(lin.proc) if type(p).__name__ != "NullCollision"]])
+    return P.CollisionTable(proc=procs, grid_kind=0, L1=lin.L1, L2=lin.L2, nE=lin.nE, rate=rate, maxrate=float(rb.max()), ratebound=rb)
+
+
+@pytest.mark.gpu
+def test_vector_rate_bound_lookup_and_replay(gctx, octx):
+    tab = _vb_table()
+    e = np.random.default_rng(8).uniform(0, 99.9, 50000) * co.eV
+    rg, bg = gctx.table_eval(tab, e)
+    ro, bo = octx.table_eval(tab, e)
+    assert np.array_equal(rg.view(np.uint64), ro.view(np.uint64))
+    assert np.array_equal(bg.view(np.uint64), bo.view(np.uint64))                    # bit-exact tier
+    grid = np.linspace(tab.L1, tab.L2, tab.nE)
+    np.testing.assert_allclose(bo, np.interp(e, grid, tab.ratebound), rtol=1e-12)   # the oracle against numpy
+    assert (bo >= rg.sum(axis=0) * (1 - 1e-12)).all()
+    n = 3000
+    rng = np.random.default_rng(4)
+    st = dict(x=np.zeros((n, 3)), p=rng.normal(size=(n, 3)) * np.sqrt(2 * 2 * co.eV / co.electron_mass), s=-np.log(1 - rng.random(n)),
+              uid=np.arange(1, n + 1, dtype=np.uint64))
+    psh = P.RK2Pusher(P.ElectromagneticField(P.HomogeneousField([0.0, 0.0, -100 * co.Td * co.nair]), None))
+    out = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(6, 0)
+        pop = P.Population(ctx, P.SLOW_ELECTRON, 3 * n, st, tab, 0.0)
+        mp = P.MultiPopulation(("slow", pop))
+        for k in range(3):
+            P.advance(mp, psh, (k + 1) * 1e-12)
+        d = pop.download()
+        o = np.argsort(d["uid"], kind="stable")
+        out.append(({k: v[o] for k, v in d.items()}, P.last_advance_stats(mp)["substeps"], ctx.error_flags()))
+    (g, sg, fg), (o, so, fo) = out
+    assert fg == 0 and fo == 0
+    assert abs(sg - so) <= 2e-3 * so + 5
+    common, ig, io = np.intersect1d(g["uid"], o["uid"], return_indices=True)
+    assert len(common) >= 0.995 * len(o["uid"])
+    scale = np.maximum(np.linalg.norm(o["p"][io], axis=1), 1e-300)[:, None]
+    bad = (np.abs(g["p"][ig] - o["p"][io]) / scale).max(axis=1) > 1e-6
+    assert bad.sum() <= max(2, 0.002 * len(common)), int(bad.sum())
+
+
+# ---------------------------------------------------------------------------------------------------
+# invariance to the partition (SURVEY section 8e): streams are keyed by uid, never by rank
+# ---------------------------------------------------------------------------------------------------
+def test_results_do_not_depend_on_how_particles_are_sharded(air_tables):
+    """The same particles (same uids, same seed) advanced in ONE context and split over TWO contexts end in identical
+    per-uid states, bit for bit, births included: nothing in the path depends on the rank or on the neighbours of a
+    particle.  (Wavefront kernel forced on every pass so that both runs take the same code path.)"""
+    def world(frac):
+        ctx = P.Context(device=0)
+        ctx.set_option("small_pass_rows", 0)
+        ctx.set_rng(5, 0)
+        mp, el, ph, po = make_world(ctx, air_tables, 6000, 3000, 600, cap=80000, seed=77)
+        if frac is not None:                      # keep one interleaved half of every species
+            for q in (el, ph, po):
+                d = q.download()
+                keep = (np.arange(len(d["uid"])) % 2) == frac
+                q.upload({k: v[keep] for k, v in d.items()})
+        return ctx, mp, (el, ph, po)
+
+    def run(ctx, mp, pops):
+        t = 0.0
+        for _ in range(3):
+            t += DT
+            P.advance(mp, default_pusher(), t)
+            for q in pops:
+                P.droplow(q)
+        out = [_by_uid(q) for q in pops]
+        ctx.close()
+        return out
+
+    whole = run(*world(None))
+    halves = [run(*world(0)), run(*world(1))]
+    for k, name in enumerate(("electron", "photon", "positron")):
+        merged = {c: np.concatenate([h[k][c] for h in halves]) for c in whole[k]}
+        o = np.argsort(merged["uid"], kind="stable")
+        assert np.array_equal(merged["uid"][o], whole[k]["uid"]), name
+        for c in whole[k]:
+            assert np.array_equal(np.ascontiguousarray(merged[c][o]).view(np.uint8), np.ascontiguousarray(whole[k][c]).view(np.uint8)), (name, c)
+
+
+def test_mixed_population_replay_at_1e5_per_species(gctx, octx, air_tables):
+    """BASELINE configs[3] (mixed e-/gamma/e+ feedback population, all nine processes) at 1e5 particles per species, one
+    step, every particle compared with the oracle by uid."""
+    worlds = []
+    for ctx in (gctx, octx):
+        ctx.set_rng(4, 0)
+        worlds.append(make_world(ctx, air_tables, 100000, 100000, 100000, cap=400000, seed=44, emin=2e3, emax=3e7))
+    for mp, *_ in worlds:
+        P.advance(mp, default_pusher(), DT)
+    sg, so = P.last_advance_stats(worlds[0][0]), P.last_advance_stats(worlds[1][0])
+    assert sg["substeps"] == so["substeps"], (sg["substeps"], so["substeps"])
+    assert sg["births"] == so["births"]
+    for k, label in ((1, "electron"), (2, "photon"), (3, "positron")):
+        _compare_populations(worlds[0][k], worlds[1][k], f"mixed1e5/{label}")
+    assert gctx.error_flags(clear=True) == octx.error_flags(clear=True) == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# statistical tier on BASELINE configs[0] (scripts/swarm.jl): independent seeds on both sides
+# ---------------------------------------------------------------------------------------------------
+def _weighted_ks(xa, wa, xb, wb):
+    """Two-sample Kolmogorov-Smirnov distance between weighted samples."""
+    xs = np.concatenate([xa, xb])
+    o = np.argsort(xs, kind="stable")
+    fa = np.concatenate([wa / wa.sum(), np.zeros(len(xb))])[o].cumsum()
+    fb = np.concatenate([np.zeros(len(xa)), wb / wb.sum()])[o].cumsum()
+    return float(np.abs(fa - fb).max())
+
+
+def _swarm_observables(ctx, tables, seed, n0=1500, nsteps=80, every=8):
+    """scripts/swarm.jl:28-98 re-expressed for the current API: electrons in a uniform field of
+    5e5 V/m along -z in STP air, dt = 2.5e-11 s, 2 ns, roulette back to n0 electrons every `every` steps."""
+    ctx.set_rng(seed, 0)
+    mp, el, ph, po = make_world(ctx, tables, n0, 0, 0, cap=40 * n0, seed=seed, espec=3e6)
+    psh = default_pusher()
+    t = 0.0
+    hist = []
+    for k in range(nsteps):
+        t += DT
+        P.advance(mp, psh, t)
+        for q in (el, ph, po):
+            P.droplow(q)
+        d = el.diag()
+        hist.append((t, d.weight, d.wx[2] / d.weight, d.wenergy / d.weight))
+        if (k + 1) % every == 0 and len(el) > n0:
+            P.roulette(n0 / len(el), el)
+            P.repack(el)
+    h = np.array(hist)
+    late = h[len(h) // 2:]
+    growth = np.polyfit(late[:, 0], np.log(late[:, 1]), 1)[0]        # d ln(W)/dt of the WEIGHTED electron number (roulette-invariant)
+    drift = np.polyfit(late[:, 0], late[:, 2], 1)[0]                 # d<z>/dt
+    d = el.download()
+    a = d["active"] == 1
+    e = P.kinenergy(P.ELECTRON, d["p"][a])
+    cost = d["p"][a][:, 2] / np.linalg.norm(d["p"][a], axis=1)
+    return {"growth": growth, "drift": drift, "meanenergy": float(late[:, 3].mean()), "e": e, "cost": cost, "w": d["w"][a],
+            "n_photons": len(ph)}
+
+
+def test_statistical_tier_swarm_over_16_seeds(air_tables):
+    """North-star statistics level: avalanche growth rate, mean energy, drift velocity within 3 sigma of the seed-to-seed
+    scatter, and KS distances of the energy and cos(theta) spectra no larger than the distances between independent halves of
+    ONE code's seeds — 16 independent seeds per side, 2 ns each, with roulette (the CUDA path never sees the oracle's seeds)."""
+    from oracle_backend import oracle_context
+    nseed = 16
+    g, o = [], []
+    for s in range(nseed):
+        ctx = P.Context(device=0)
+        g.append(_swarm_observables(ctx, air_tables, 1000 + s))
+        ctx.close()
+        ctx = oracle_context()
+        o.append(_swarm_observables(ctx, air_tables, 2000 + s))
+        ctx.close()
+    report = {}
+    for key in ("growth", "drift", "meanenergy"):
+        a, b = np.array([r[key] for r in g]), np.array([r[key] for r in o])
+        sigma = np.sqrt(a.var(ddof=1) / nseed + b.var(ddof=1) / nseed)
+        report[key] = (a.mean(), b.mean(), sigma)
+        assert abs(a.mean() - b.mean()) <= 3 * sigma, (key, a.mean(), b.mean(), sigma)
+    assert 0 < report["drift"][0] < co.c                              # electrons drift against the field (E along -z), slower than light
+    pool = lambda rs, key: np.concatenate([r[key] for r in rs])
+    for key in ("e", "cost"):
+        d_go = _weighted_ks(pool(g, key), pool(g, "w"), pool(o, key), pool(o, "w"))
+        d_gg = _weighted_ks(pool(g[::2], key), pool(g[::2], "w"), pool(g[1::2], key), pool(g[1::2], "w"))
+        d_oo = _weighted_ks(pool(o[::2], key), pool(o[::2], "w"), pool(o[1::2], key), pool(o[1::2], "w"))
+        report["ks_" + key] = (d_go, d_gg, d_oo)
+        # independent halves of one code differ by d_gg / d_oo from seed scatter alone (families of an avalanche are
+        # correlated, so the textbook critical value does not apply); the two codes must not differ by more than that
+        assert d_go <= 1.5 * max(d_gg, d_oo) + 0.01, (key, d_go, d_gg, d_oo)
+    print("[statistics]", {k: tuple(float(f"{x:.5g}") for x in v) for k, v in report.items()})

@@ -565,3 +565,36 @@ def test_rng_step_makes_results_reproducible(octx, air_tables):
         assert ctx.get_rng() == (9, 5)
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_energy_law_roulette_preserves_expected_weight(octx, air_tables):
+    """roulette!(f, popl) with an energy-dependent retain probability: survivors carry w / p(E), so the total weight is
+    conserved in expectation in every energy band (population.jl:291-309)."""
+    rng = np.random.default_rng(1)
+    n = 60000
+    K = np.exp(rng.uniform(np.log(2e3), np.log(1e7), n)) * co.eV
+    pn = P.momentum_norm_from_kin(P.ELECTRON, K)
+    st = dict(x=np.zeros((n, 3)), p=np.stack([np.zeros(n), np.zeros(n), pn], axis=1), w=np.ones(n))
+    pop = P.Population(octx, P.ELECTRON, n + 10, st, air_tables["electron"], 1e3 * co.eV)
+    law = lambda e: 0.1 + 0.9 * min(1.0, e / (1e6 * co.eV))
+    P.roulette(law, pop, lo=1e3 * co.eV, hi=1e7 * co.eV, nodes=2049, logscale=False)
+    d = pop.download()
+    for lo_e, hi_e in [(2e3, 1e5), (1e5, 1e6), (1e6, 1e7)]:
+        m = (K > lo_e * co.eV) & (K < hi_e * co.eV)
+        w_after = d["w"][m][d["active"][m] == 1].sum()
+        assert abs(w_after / m.sum() - 1) < 0.05, (lo_e, w_after / m.sum())
+    assert d["active"][K > 1e6 * co.eV].all()
+
+
+def test_shuffle_is_a_uniformish_permutation(octx, air_tables):
+    n = 20000
+    st = dict(x=np.zeros((n, 3)), p=np.tile([0, 0, 3e-22], (n, 1)), uid=np.arange(1, n + 1, dtype=np.uint64))
+    pop = P.Population(octx, P.ELECTRON, n, st, air_tables["electron"], 1e3 * co.eV)
+    octx.set_rng(5, 0)
+    P.shuffle(pop)
+    u = pop.download()["uid"].astype(np.int64)
+    assert sorted(u.tolist()) == list(range(1, n + 1))
+    # displacement statistics of a uniform random permutation: mean |i - pi(i)| = n/3, correlation ~ 0
+    disp = np.abs(u - 1 - np.arange(n)).mean()
+    assert abs(disp / (n / 3) - 1) < 0.05
+    assert abs(np.corrcoef(u, np.arange(n))[0, 1]) < 0.03
