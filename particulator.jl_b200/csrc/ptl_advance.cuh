@@ -102,10 +102,14 @@ __device__ __forceinline__ unsigned long long coast_below_cut(const AdvanceParam
     return nsub;
 }
 
+// `rows_per_warp` (1..32): how many lanes of a warp carry a particle.  A lane-per-particle warp executes the UNION of its lanes'
+// control flow, so one loop iteration costs push + every process branch some lane takes; in the latency regime (a pass of a few
+// thousand rows, bound by the ~400-collision chain of its slowest particle) giving every particle a warp of its own halves the
+// time per sub-step.  The launcher picks the smallest value that still fills the machine.
 template <int SP, bool FIRST, bool CB>
 __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                          unsigned long long* tile_counter, const long long* __restrict__ rows,
-                                                         const unsigned long long* __restrict__ nrows) {
+                                                         const unsigned long long* __restrict__ nrows, const int rows_per_warp) {
     // index-list mode: process rows[0 .. *nrows) (the particles the streaming kernel deferred) instead of [i0, i1)
     if (rows != nullptr) { i0 = 0; i1 = (long long)*nrows; }
     extern __shared__ double smem[];
@@ -141,10 +145,10 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
         long long tile = 0;
         if (lane == 0) tile = (long long)atomicAdd(tile_counter, 1ULL);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        long long base = i0 + tile * 32;
+        long long base = i0 + tile * rows_per_warp;
         if (base >= i1) break;
         long long i = base + lane;
-        if (i >= i1) continue;
+        if (lane >= rows_per_warp || i >= i1) continue;
         if (rows != nullptr) i = rows[i];
         if (!Q.active[i]) continue;    // l.active || continue   mixed_population.jl:63
 
@@ -279,7 +283,11 @@ constexpr int STREAM_THREADS = 256;
 template <int SP, bool FIRST>
 // (No minimum-blocks bound on purpose: ptxas picks 118 registers, 2 CTAs per SM, 0.39 ms for 2e7 photons = 87 % of the
 // measured HBM bandwidth.  Forcing 3 or 4 CTAs (80 / 64 registers, spills) measured 0.41 / 0.43 ms; (256, 1) 0.61 ms.)
-__global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+// Leptons (species that a force acts on) carry the RK2 push and the rate-bound lookup: two of them per thread took 216
+// registers, ONE 256-thread CTA per SM, and the kernel could not cover the HBM latency (48 % of the measured bandwidth at
+// kappa ~ 1).  They go one particle per thread (STREAM_NP = 1: 64-bit accesses, still one full 256-byte span per warp and
+// column) at three CTAs per SM; photons keep two per thread and 128-bit accesses.
+__global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 2 : 3) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                                   long long* __restrict__ slow_rows, unsigned long long* slow_count) {
     extern __shared__ double smem[];
     const TableView& T = P.tab[SP];
@@ -295,10 +303,11 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_
     }
     __syncthreads();
     unsigned long long nsub = 0;
-    const long long npairs = (i1 - i0 + 1) / 2;
+    constexpr int NP = (SP == PTL_PHOTON) ? 2 : 1;      // particles per thread
+    const long long npairs = (i1 - i0 + NP - 1) / NP;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < npairs; q += (long long)gridDim.x * blockDim.x) {
-        const long long i = i0 + 2 * q;          // i0 is even (rows of a pass start at 0 or at an even boundary, see launcher)
-        const bool two = i + 1 < i1;
+        const long long i = i0 + NP * q;         // i0 is even (rows of a pass start at 0 or at an even boundary, see launcher)
+        const bool two = NP == 2 && i + 1 < i1;
         double2 c[9];
         unsigned char a0, a1 = 0;
         if (two) {
@@ -317,7 +326,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_
             }
             a0 = Q.active[i];
         }
-        double xs[2][3], ts[2], ss[2], rs[2];
+        double xs[2][3], ps[2][3], ts[2], ss[2], rs[2];
         bool wr[2] = {false, false}, wr_r[2] = {false, false};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -344,9 +353,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_
             xs[h][0] = x.x; xs[h][1] = x.y; xs[h][2] = x.z; ts[h] = t; ss[h] = s; rs[h] = r;
             wr[h] = true;
             wr_r[h] = FIRST && r != r0;
-            if (SP != PTL_PHOTON) {                               // species whose momentum changes under the pusher
-                Q.col[COL_P0][i + h] = p.x; Q.col[COL_P1][i + h] = p.y; Q.col[COL_P2][i + h] = p.z;
-            }
+            if (SP != PTL_PHOTON) { ps[h][0] = p.x; ps[h][1] = p.y; ps[h][2] = p.z; }   // species whose momentum changes under the pusher
         }
         if (two && wr[0] && wr[1]) {
             *reinterpret_cast<double2*>(Q.col[COL_X0] + i) = make_double2(xs[0][0], xs[1][0]);
@@ -354,12 +361,18 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_advance_stream(const __grid_
             *reinterpret_cast<double2*>(Q.col[COL_X2] + i) = make_double2(xs[0][2], xs[1][2]);
             *reinterpret_cast<double2*>(Q.col[COL_T] + i) = make_double2(ts[0], ts[1]);
             *reinterpret_cast<double2*>(Q.col[COL_S] + i) = make_double2(ss[0], ss[1]);
+            if (SP != PTL_PHOTON) {
+                *reinterpret_cast<double2*>(Q.col[COL_P0] + i) = make_double2(ps[0][0], ps[1][0]);
+                *reinterpret_cast<double2*>(Q.col[COL_P1] + i) = make_double2(ps[0][1], ps[1][1]);
+                *reinterpret_cast<double2*>(Q.col[COL_P2] + i) = make_double2(ps[0][2], ps[1][2]);
+            }
         } else {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 if (!wr[h]) continue;
                 Q.col[COL_X0][i + h] = xs[h][0]; Q.col[COL_X1][i + h] = xs[h][1]; Q.col[COL_X2][i + h] = xs[h][2];
                 Q.col[COL_T][i + h] = ts[h]; Q.col[COL_S][i + h] = ss[h];
+                if (SP != PTL_PHOTON) { Q.col[COL_P0][i + h] = ps[h][0]; Q.col[COL_P1][i + h] = ps[h][1]; Q.col[COL_P2][i + h] = ps[h][2]; }
             }
         }
 #pragma unroll

@@ -67,6 +67,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
         if (!strcmp(km, "nostream")) ctx->use_stream = false;
     }
     if (const char* sp = getenv("PTL_SMALL_PASS")) ctx->small_pass_rows = atoll(sp);
+    if (const char* ov = getenv("PTL_OVERLAP")) ctx->overlap_species = atoi(ov) != 0;
     if (stream) {
         ctx->stream = (cudaStream_t)stream;
     } else {
@@ -79,6 +80,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     }
     cudaMemsetAsync(ctx->d_sc, 0, sizeof(DeviceScalars), ctx->stream);
     memset(ctx->h_sc, 0, sizeof(DeviceScalars));
+    ctx->lstream = ctx->stream;
     ctx->partial_blocks = ctx->sm_count * 8;
     if (cudaMalloc(&ctx->d_partial, sizeof(double) * DIAG_NVAL * ctx->partial_blocks) != cudaSuccess) { delete ctx; return PTL_ENOMEM; }
     cudaStreamSynchronize(ctx->stream);
@@ -98,7 +100,13 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     for (auto& w : ctx->walls) if (w.block) cudaFree(w.block);
     for (int b = 0; b < 2; b++) if (ctx->stage[b]) cudaFree(ctx->stage[b]);
     cudaFree(ctx->d_tile_counts); cudaFree(ctx->d_tile_offsets); cudaFree(ctx->d_holes); cudaFree(ctx->d_tails);
-    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp); cudaFree(ctx->d_slow_rows); cudaFree(ctx->d_coll);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_tmp); cudaFree(ctx->d_coll);
+    for (int k = 0; k < PTL_NSPECIES; k++) {
+        cudaFree(ctx->d_slow_rows[k]);
+        if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+        if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->d_sc);
     cudaFreeHost(ctx->h_sc);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
@@ -143,6 +151,7 @@ EXPORT int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value)
         return 0;
     }
     if (!strcmp(name, "stream")) { ctx->use_stream = value != 0; return 0; }
+    if (!strcmp(name, "overlap")) { ctx->overlap_species = value != 0; return 0; }
     if (!strcmp(name, "small_pass_rows")) { if (value < 0) return PTL_EINVAL; ctx->small_pass_rows = value; return 0; }
     ctx->err = std::string("unknown option ") + name;
     return PTL_EINVAL;
@@ -922,6 +931,25 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
             tprev = tnow; sub_prev = sub;
         }
         long long total = 0;
+        // The species of one pass are independent of each other: a kernel visits rows [iup, n) of its own population and
+        // births only append beyond n.  So the kernels of a pass run concurrently — the first species on the context's
+        // stream, the others on auxiliary streams forked from it and joined back before the counters are read.  In the
+        // latency regime (a few thousand rows, bound by the collision chain of the slowest particle) the chains of the
+        // species overlap instead of adding up.  (Sequential when a population overflowed: its count is being clamped.)
+        bool clamp = false;
+        int nlaunch = 0;
+        for (int pi : M.pops) {
+            Pop& P = ctx->pops[pi];
+            long long n = (long long)ctx->h_sc->pop_n[P.slot];
+            if (n > P.v.capacity) clamp = true;
+            if ((n > P.v.capacity ? P.v.capacity : n) - P.iup > 0) nlaunch++;
+        }
+        const bool overlap = ctx->overlap_species && !clamp && nlaunch > 1;
+        if (overlap) {
+            if (!ctx->ev_fork) CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        }
+        int launched = 0;
         for (int pi : M.pops) {
             Pop& P = ctx->pops[pi];
             long long n = (long long)ctx->h_sc->pop_n[P.slot];
@@ -932,8 +960,24 @@ EXPORT int32_t ptl_advance(ptl_context* ctx, int32_t mp, const ptl_pusher_desc* 
             long long rows = n - P.iup;
             if (rows > 0) {
                 const Table& T = ctx->tables[P.table];
-                rc = launch_advance(ctx, P.v.species, A, P.iup, n, first, has_cb, T.smem_bytes, first && P.kappa_est >= 0 && P.kappa_est < 2.0);
+                const int sp = P.v.species;
+                ctx->lstream = ctx->stream;
+                if (overlap && launched > 0) {
+                    if (!ctx->aux[sp]) {
+                        CK(cudaStreamCreateWithFlags(&ctx->aux[sp], cudaStreamNonBlocking));
+                        CK(cudaEventCreateWithFlags(&ctx->ev_join[sp], cudaEventDisableTiming));
+                    }
+                    ctx->lstream = ctx->aux[sp];
+                    CK(cudaStreamWaitEvent(ctx->lstream, ctx->ev_fork, 0));
+                }
+                rc = launch_advance(ctx, sp, A, P.iup, n, first, has_cb, T.smem_bytes, first && P.kappa_est >= 0 && P.kappa_est < 2.0);
+                if (ctx->lstream != ctx->stream) {
+                    CK(cudaEventRecord(ctx->ev_join[sp], ctx->lstream));
+                    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[sp], 0));
+                }
+                ctx->lstream = ctx->stream;
                 if (rc) return rc;
+                launched++;
                 total += rows;
                 ctx->stats.rows += rows;
                 P.rows_last += rows;

@@ -22,7 +22,7 @@ namespace ptl_host {
 struct DeviceScalars {            // one small device block mirrored in pinned host memory
     int flags;
     int _pad;
-    unsigned long long substeps[PTL_NSPECIES], births, tile_counter, total, nmoves, slow_count, max_uid;
+    unsigned long long substeps[PTL_NSPECIES], births, tile_counter[PTL_NSPECIES], total, nmoves, slow_count[PTL_NSPECIES], max_uid;
     unsigned long long pop_n[64];
     unsigned long long wall_n[PTL_MAX_WALLS];
     double diag[ptl::DIAG_NVAL_HOST];
@@ -95,8 +95,14 @@ struct ptl_context {
     int partial_blocks = 0;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
-    long long* d_slow_rows = nullptr;  // rows the streaming photon kernel deferred to the general kernel
-    size_t slow_cap = 0;
+    long long* d_slow_rows[PTL_NSPECIES] = {nullptr, nullptr, nullptr, nullptr};  // rows the streaming kernel of a species deferred to its general kernel
+    size_t slow_cap[PTL_NSPECIES] = {0, 0, 0, 0};
+    // species of one pass of advance1! are independent (births only append beyond the rows a pass visits): their kernels run
+    // concurrently, the first on the context's stream and the others on auxiliary streams forked from / joined to it
+    cudaStream_t lstream = nullptr;    // stream the advance launchers use right now
+    cudaStream_t aux[PTL_NSPECIES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[PTL_NSPECIES] = {nullptr, nullptr, nullptr, nullptr};
+    bool overlap_species = true;       // ptl_set_option "overlap" (0: every kernel of a pass on one stream, in tuple order)
     int lepton_kernel = 0;             // 0 = default (PTL_DEFAULT_LEPTON_KERNEL), 3 = bq, 4 = wf, 5 = wq (ptl_set_option "kernel" / PTL_KERNEL)
     long long small_pass_rows = 16384; // lepton passes with fewer rows run on the one-particle-per-lane kernel (chain latency, not throughput)
     bool use_stream = true;            // streaming fast path for low-kappa species (ptl_set_option "stream" / PTL_KERNEL=nostream)

@@ -22,16 +22,24 @@ int32_t launch_advance_t(ptl_context* ctx, const AdvanceParams& A, long long i0,
     int blocks_per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, ADV_THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
         blocks_per_sm = 1;
-    long long tiles = (i1 - i0 + 31) / 32;
+    // lanes per warp that carry a particle: as few as still give every resident warp of the machine something to do
+    // (index-list mode does not know its row count on the host: full warps)
+    const long long machine_warps = (long long)ctx->sm_count * blocks_per_sm * (ADV_THREADS / 32);
+    int rpw = 32;
+    if (rows == nullptr) {
+        long long q = (i1 - i0 + machine_warps - 1) / machine_warps;
+        rpw = q < 1 ? 1 : (q > 32 ? 32 : (int)q);
+    }
+    long long tiles = (i1 - i0 + rpw - 1) / rpw;
     long long want = (tiles + (ADV_THREADS / 32) - 1) / (ADV_THREADS / 32);
     long long grid = (long long)ctx->sm_count * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter[SP], 0, sizeof(unsigned long long), ctx->lstream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
+    kern<<<(unsigned)grid, ADV_THREADS, smem, ctx->lstream>>>(A, i0, i1, &ctx->d_sc->tile_counter[SP], rows, rows ? &ctx->d_sc->slow_count[SP] : nullptr, rpw);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
     return 0;
@@ -55,11 +63,11 @@ int32_t launch_advance_wf_k(ptl_context* ctx, const AdvanceParams& A, long long 
     long long grid = (long long)ctx->sm_count * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter[SP], 0, sizeof(unsigned long long), ctx->lstream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
+    kern<<<(unsigned)grid, WF_THREADS, smem, ctx->lstream>>>(A, i0, i1, &ctx->d_sc->tile_counter[SP], rows, rows ? &ctx->d_sc->slow_count[SP] : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
     return 0;
@@ -82,11 +90,11 @@ int32_t launch_advance_bq_k(ptl_context* ctx, const AdvanceParams& A, long long 
     long long grid = (long long)ctx->sm_count * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter[SP], 0, sizeof(unsigned long long), ctx->lstream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, BQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
+    kern<<<(unsigned)grid, BQ_THREADS, smem, ctx->lstream>>>(A, i0, i1, &ctx->d_sc->tile_counter[SP], rows, rows ? &ctx->d_sc->slow_count[SP] : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
     return 0;
@@ -111,11 +119,11 @@ int32_t launch_advance_wq_k(ptl_context* ctx, const AdvanceParams& A, long long 
     long long grid = (long long)ctx->sm_count * blocks_per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter, 0, sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(&ctx->d_sc->tile_counter[SP], 0, sizeof(unsigned long long), ctx->lstream));
     bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-    kern<<<(unsigned)grid, WQ_THREADS, smem, ctx->stream>>>(A, i0, i1, &ctx->d_sc->tile_counter, rows, rows ? &ctx->d_sc->slow_count : nullptr);
-    if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+    if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
+    kern<<<(unsigned)grid, WQ_THREADS, smem, ctx->lstream>>>(A, i0, i1, &ctx->d_sc->tile_counter[SP], rows, rows ? &ctx->d_sc->slow_count[SP] : nullptr);
+    if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
     LAUNCHED();
     ctx->stats.launches++;
     return 0;
@@ -147,30 +155,31 @@ int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0,
     const long long* rows = nullptr;
     if ((SP == PTL_PHOTON || low_kappa) && !cb && (i0 & 1) == 0 && i1 - i0 >= 4096 && ctx->use_stream) {
         size_t need = (size_t)(i1 - i0);
-        if (need > ctx->slow_cap) {
-            cudaFree(ctx->d_slow_rows);
-            ctx->d_slow_rows = nullptr; ctx->slow_cap = 0;
+        if (need > ctx->slow_cap[SP]) {
+            cudaFree(ctx->d_slow_rows[SP]);
+            ctx->d_slow_rows[SP] = nullptr; ctx->slow_cap[SP] = 0;
             // grow geometrically (x2, at least 4 Mi entries): a photon population that grows every step must not pay a
             // cudaFree/cudaMalloc pair inside most advance! calls (each one synchronises the device)
             size_t cap = need * 2 > ((size_t)4 << 20) ? need * 2 : ((size_t)4 << 20);
-            CK(cudaMalloc(&ctx->d_slow_rows, sizeof(long long) * cap));
-            ctx->slow_cap = cap;
+            CK(cudaMalloc(&ctx->d_slow_rows[SP], sizeof(long long) * cap));
+            ctx->slow_cap[SP] = cap;
         }
-        CK(cudaMemsetAsync(&ctx->d_sc->slow_count, 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(&ctx->d_sc->slow_count[SP], 0, sizeof(unsigned long long), ctx->lstream));
         const TableView& TV = A.tab[SP];
         size_t ssm = TV.kind == 0 ? sizeof(double) * TV.order * (TV.k + 1) : 8;
-        long long pairs = (i1 - i0 + 1) / 2;
+        constexpr int np = (SP == PTL_PHOTON) ? 2 : 1;      // particles per thread (k_advance_stream)
+        long long pairs = (i1 - i0 + np - 1) / np;
         long long grid = (pairs + STREAM_THREADS - 1) / STREAM_THREADS;
         long long maxgrid = (long long)ctx->sm_count * 8;
         if (grid > maxgrid) grid = maxgrid;
         bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
-        if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->stream); }
-        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-        else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->stream>>>(A, i0, i1, ctx->d_slow_rows, &ctx->d_sc->slow_count);
-        if (timed) { cudaEventRecord(ctx->ev1, ctx->stream); ctx->ev_pending = true; }
+        if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
+        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+        else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+        if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
         LAUNCHED();
         ctx->stats.launches++;
-        rows = ctx->d_slow_rows;
+        rows = ctx->d_slow_rows[SP];
         cb = false;
     }
     // Small passes (the newborns of a step, the reference's own 1e4-electron swarms) are bound by the sequential chain of
