@@ -594,24 +594,32 @@ def main():
         t_loc = float(host["t"][0]) + DT
         errors = []
 
+        phase_ms = [[0.0, 0.0, 0.0] for _ in range(nworkers)]      # upload / advance+droplow / download wall time per worker (last step)
+
         def work(wk):
             wctx, wmp, wel, pd = workers[wk]
+            phase_ms[wk][:] = [0.0, 0.0, 0.0]
             try:
                 for sh in range(wk, nshards, nworkers):
                     lo, m = bounds[sh], bounds[sh + 1] - bounds[sh]
+                    tp0 = time.perf_counter()
                     rc = b.population_upload(wctx.h, wel.id, m, ptr(host["x"], C.c_double, lo), ptr(host["p"], C.c_double, lo),
                                              ptr(host["w"], C.c_double, lo), ptr(host["t"], C.c_double, lo), ptr(host["s"], C.c_double, lo),
                                              ptr(host["r"], C.c_double, lo), ptr(host["active"], C.c_uint8, lo), ptr(host["uid"], C.c_uint64, lo))
                     assert rc == 0, rc
+                    tp1 = time.perf_counter()
                     rc = b.advance(wctx.h, wmp.id, C.byref(pd), t_loc, None)
                     assert rc >= 0, rc
                     for q in wmp:
                         b.droplow(wctx.h, q.id, 0.0)
+                    tp2 = time.perf_counter()
                     o = out[sh]
                     got_rows[sh] = int(b.population_download(wctx.h, wel.id, out_cap[sh], ptr(o["x"], C.c_double), ptr(o["p"], C.c_double),
                                                              ptr(o["w"], C.c_double), ptr(o["t"], C.c_double), ptr(o["s"], C.c_double),
                                                              ptr(o["r"], C.c_double), ptr(o["active"], C.c_uint8), ptr(o["uid"], C.c_uint64)))
                     assert got_rows[sh] > 0
+                    tp3 = time.perf_counter()
+                    phase_ms[wk][0] += (tp1 - tp0) * 1e3; phase_ms[wk][1] += (tp2 - tp1) * 1e3; phase_ms[wk][2] += (tp3 - tp2) * 1e3
                     # photons / positrons born in this shard stay on the device (they are results of later steps' inputs)
                     b.population_clear(wctx.h, list(wmp)[1].id)
                     b.population_clear(wctx.h, list(wmp)[2].id)
@@ -648,7 +656,9 @@ def main():
                "ms_per_step": float(e2e_ms.item()) / max(args.e2e_steps, 1),
                "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download, "
                        f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other)",
-               "timer": "host wall clock between device-wide synchronizes (work spans several streams)"}
+               "timer": "host wall clock between device-wide synchronizes (work spans several streams)",
+               "worker_phase_ms_last_step": {"upload": [round(p[0], 1) for p in phase_ms], "advance_droplow": [round(p[1], 1) for p in phase_ms],
+                                             "download": [round(p[2], 1) for p in phase_ms]}}
         for wctx, *_ in workers:
             wctx.close()
 

@@ -157,7 +157,10 @@ class Backend:
         self.fn = {}
         sigs = dict(_SIGS)
         sigs.update({k: v for k, v in _SIGS_DEVICE_ONLY.items() if hasattr(self.dll, prefix + k)})
+        tolerant = bool(os.environ.get("PTL_AB_OLD_LIB"))     # development aid: A/B against a library built from an older commit
         for name, (res, args) in sigs.items():
+            if tolerant and not hasattr(self.dll, prefix + name):
+                continue
             f = getattr(self.dll, prefix + name)
             f.restype = res
             if args is not None:

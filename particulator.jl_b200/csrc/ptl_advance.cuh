@@ -287,7 +287,7 @@ template <int SP, bool FIRST>
 // registers, ONE 256-thread CTA per SM, and the kernel could not cover the HBM latency (48 % of the measured bandwidth at
 // kappa ~ 1).  They go one particle per thread (STREAM_NP = 1: 64-bit accesses, still one full 256-byte span per warp and
 // column) at three CTAs per SM; photons keep two per thread and 128-bit accesses.
-__global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 2 : 3) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+__global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                                   long long* __restrict__ slow_rows, unsigned long long* slow_count) {
     extern __shared__ double smem[];
     const TableView& T = P.tab[SP];

@@ -42,6 +42,9 @@ namespace ptl {
 #ifndef WQ_LOAD_WEIGHT
 #define WQ_LOAD_WEIGHT 8                // score per pending LOAD / LOADWAIT entry (8 = like every other class)
 #endif
+#ifndef WQ_COUNT64
+#define WQ_COUNT64 0                    // 1: one 64-bit one-hot add per slot instead of two 32-bit selects (measured: no faster)
+#endif
 #ifndef WQ_SYNC
 #define WQ_SYNC 0                       // 0: autonomous warps (default); 1: the warps of a group agree on one class per round (one barrier)
 #endif
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const 
         // class populations of this warp's pool: every lane adds a one-hot byte per owned slot (class c -> byte c of a
         // 64-bit word; retired slots land in the unused byte 6), two REDUX adds sum the halves over the warp
         uint32_t cls[WQ_K];
+#if WQ_COUNT64
         unsigned long long oh = 0;
 #pragma unroll
         for (int k = 0; k < WQ_K; k++) {
@@ -162,6 +166,17 @@ __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const 
         }
         const uint32_t pa = __reduce_add_sync(0xffffffffu, (uint32_t)oh);            // LOAD, STEP, COULOMB, RBEB
         const uint32_t pb = __reduce_add_sync(0xffffffffu, (uint32_t)(oh >> 32)) & 0xffffu;   // LOADWAIT, OTHER
+#else
+        uint32_t pa = 0, pb = 0;
+#pragma unroll
+        for (int k = 0; k < WQ_K; k++) {
+            cls[k] = S.state[base + 32 * k + lane] & 0xffu;
+            pa += cls[k] < 4u ? (1u << (8 * cls[k])) : 0u;                          // LOAD, STEP, COULOMB, RBEB
+            pb += (cls[k] == WS_LOADWAIT) ? 1u : (cls[k] == WS_OTHER ? 256u : 0u);
+        }
+        pa = __reduce_add_sync(0xffffffffu, pa);
+        pb = __reduce_add_sync(0xffffffffu, pb);
+#endif
         // lane c: population of class c in this warp's pool, capped at one chunk
         const int n_c = lane < WS_IDLE ? (int)(((lane < 4 ? pa : pb) >> (8 * (lane & 3))) & 0xffu) : 0;
         const int f_c = n_c < 32 ? n_c : 32;

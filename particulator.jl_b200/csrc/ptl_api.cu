@@ -110,6 +110,7 @@ EXPORT int32_t ptl_context_destroy(ptl_context* ctx) {
     cudaFree(ctx->d_sc);
     cudaFreeHost(ctx->h_sc);
     if (ctx->ev0) { cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); }
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -401,21 +402,34 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
     if (!P) return PTL_EHANDLE;
     if (n < 0 || n > P->v.capacity) return PTL_EINVAL;
     if (n > 0 && (!x3 || !p3 || !w || !t || !s || !r || !active)) return PTL_EINVAL;
-    int32_t rc = ensure_stage(ctx); if (rc) return rc;
-    // x, p: host xyz-interleaved -> planar columns, chunked through two staging buffers
-    int b = 0;
-    for (int which = 0; which < 2; which++) {
-        const double* src = which == 0 ? x3 : p3;
-        int c0 = which == 0 ? COL_X0 : COL_P0;
-        for (long long off = 0; off < n; off += (long long)ctx->stage_rows) {
-            long long m = n - off < (long long)ctx->stage_rows ? n - off : (long long)ctx->stage_rows;
-            CK(cudaMemcpyAsync(ctx->stage[b], src + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
-            k_aos3_to_planar<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[b], P->v.col[c0] + off, P->v.col[c0 + 1] + off,
-                                                                        P->v.col[c0 + 2] + off, m);
-            LAUNCHED();
-            b ^= 1;
+    int32_t rc = ensure_stage(ctx, (size_t)n); if (rc) return rc;
+    // x, p: host xyz-interleaved -> planar columns through the staging buffers.  When a buffer holds the whole vector (x in
+    // stage[0], p in stage[1]) the copies are issued first and the transposes after them: the host arrays are borrowed only
+    // until the COPIES are done, and a copy needs no SM — the call does not have to wait for transposes that may be queued
+    // behind another context's advance kernel (persistent CTAs that fill every SM).  With several contexts pipelining
+    // shards through one GPU this took the upload of a shard from 70 ms (waiting for SMs) to the PCIe time.
+    const bool whole = (size_t)n <= ctx->stage_rows;
+    if (whole) {
+        if (n > 0) {
+            CK(cudaMemcpyAsync(ctx->stage[0], x3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->stage[1], p3, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    } else {
+        int b = 0;
+        for (int which = 0; which < 2; which++) {
+            const double* src = which == 0 ? x3 : p3;
+            int c0 = which == 0 ? COL_X0 : COL_P0;
+            for (long long off = 0; off < n; off += (long long)ctx->stage_rows) {
+                long long m = n - off < (long long)ctx->stage_rows ? n - off : (long long)ctx->stage_rows;
+                CK(cudaMemcpyAsync(ctx->stage[b], src + 3 * off, sizeof(double) * 3 * m, cudaMemcpyHostToDevice, ctx->stream));
+                k_aos3_to_planar<<<grid_for(m, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[b], P->v.col[c0] + off, P->v.col[c0 + 1] + off,
+                                                                            P->v.col[c0 + 2] + off, m);
+                LAUNCHED();
+                b ^= 1;
+            }
         }
     }
+    bool uid_kernel = false;
     if (n > 0) {
         CK(cudaMemcpyAsync(P->v.col[COL_W], w, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(P->v.col[COL_T], t, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -424,10 +438,7 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
         CK(cudaMemcpyAsync(P->v.active, active, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
         if (uid) {   // explicit uids: the default-uid counter must end up past the largest sequential one (folded in lazily)
             CK(cudaMemcpyAsync(P->v.uid, uid, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-            int blocks = (int)((n + 1023) / 1024);
-            if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-            k_uid_max<<<blocks, 256, 0, ctx->stream>>>(P->v.uid, n, &ctx->d_sc->max_uid);
-            LAUNCHED();
+            uid_kernel = true;
         } else {
             rc = refresh_next_uid(ctx); if (rc) return rc;
             k_fill_uid<<<grid_for(n, 256), 256, 0, ctx->stream>>>(P->v.uid, ctx->next_uid, n);
@@ -435,9 +446,24 @@ EXPORT int32_t ptl_population_upload(ptl_context* ctx, int32_t pop, int64_t n, c
             ctx->next_uid += (uint64_t)n;
         }
     }
+    // every byte of the host arrays has been read once this event fires
+    if (!ctx->ev_copy) CK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    if (whole && n > 0) {
+        k_aos3_to_planar<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[0], P->v.col[COL_X0], P->v.col[COL_X1], P->v.col[COL_X2], n);
+        LAUNCHED();
+        k_aos3_to_planar<<<grid_for(n, 256), 256, 0, ctx->stream>>>((const double*)ctx->stage[1], P->v.col[COL_P0], P->v.col[COL_P1], P->v.col[COL_P2], n);
+        LAUNCHED();
+    }
+    if (uid_kernel) {
+        int blocks = (int)((n + 1023) / 1024);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        k_uid_max<<<blocks, 256, 0, ctx->stream>>>(P->v.uid, n, &ctx->d_sc->max_uid);
+        LAUNCHED();
+    }
     P->iup = 0;
     rc = set_n(ctx, *P, n); if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));   // host arrays are only borrowed for the duration of the call
+    CK(cudaEventSynchronize(ctx->ev_copy));     // host arrays are only borrowed for the duration of the call
     return 0;
 }
 

@@ -110,6 +110,7 @@ struct ptl_context {
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_pending = false;
+    cudaEvent_t ev_copy = nullptr;     // "the host arrays of this upload have been read"
     // multi-GPU (ptl_comm.cu): NCCL communicator bound at run time, this context's rank, a small device scratch
     void* comm = nullptr;
     int rank = 0, nranks = 1;
@@ -167,10 +168,18 @@ inline int32_t set_n(ptl_context* ctx, Pop& P, long long n) {
     return 0;
 }
 
-inline int32_t ensure_stage(ptl_context* ctx) {
-    const size_t rows = (size_t)1 << 22;   // 4 Mi rows x 24 B = 96 MiB per staging buffer
+// Two staging buffers for the xyz-interleaved host vectors.  They hold `want` rows each when that is at most 16 Mi rows (384 MiB
+// per buffer): an upload of that size then needs no buffer reuse, so its host->device copies do not wait for any kernel and the
+// call can hand the borrowed host arrays back as soon as the COPIES are done (see ptl_population_upload).  Larger transfers go
+// through 4 Mi-row chunks that alternate between the buffers.
+inline int32_t ensure_stage(ptl_context* ctx, size_t want = 0) {
+    const size_t chunk = (size_t)1 << 22, big = (size_t)1 << 24;
+    size_t rows = want <= chunk ? chunk : (want <= big ? want : chunk);
     if (ctx->stage_rows >= rows) return 0;
-    for (int b = 0; b < 2; b++) CK(cudaMalloc(&ctx->stage[b], rows * 3 * sizeof(double)));
+    for (int b = 0; b < 2; b++) {
+        if (ctx->stage[b]) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->stage[b]); ctx->stage[b] = nullptr; }
+        CK(cudaMalloc(&ctx->stage[b], rows * 3 * sizeof(double)));
+    }
     ctx->stage_rows = rows;
     return 0;
 }

@@ -51,5 +51,6 @@ def run(dt, n, steps=4, warmup=3, spectrum_emin=1e3):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
-    for scale in (1 / 2048, 1 / 256, 1 / 32, 1 / 4, 1.0, 4.0):
+    scales = (1 / 2048,) if len(sys.argv) > 2 and sys.argv[2] == "one" else (1 / 2048, 1 / 256, 1 / 32, 1 / 4, 1.0, 4.0)
+    for scale in scales:
         print(json.dumps(run(2.5e-11 * scale, n)), flush=True)
