@@ -108,8 +108,14 @@ static __device__ __noinline__ unsigned long long wf_coast_below_cut(const Advan
 // setr! for the common table shape (Chebyshev, order 3), inline on the shared-memory rate-bound rows: ~55 instructions.
 // The generic setr<SP> is an out-of-line call that reads AdvanceParams through a generic pointer and carries the
 // any-order loop and the IEEE-division fallback (112 executed instructions per call, 6 % of the kernel in ncu).
+// (Measured: as a real function, -DPTL_SETR3_NOINLINE, 29.7 ms against 27.6 ms inline for the main pass of 4e6 electrons.)
 template <int SP>
-__device__ __forceinline__ double wf_setr_cheb3(const AdvanceParams& P, const TableView& T, const double* __restrict__ rb, double cut, Vec3 p) {
+#ifdef PTL_SETR3_NOINLINE
+__device__ __noinline__ double wf_setr_cheb3(
+#else
+__device__ __forceinline__ double wf_setr_cheb3(
+#endif
+const AdvanceParams& P, const TableView& T, const double* __restrict__ rb, double cut, Vec3 p) {
     const double eng = kinenergy<SP>(p);
     if (eng < cut) return 0.0;                                                         // collisions.jl:66
     const Pre pre = precheb(eng, T.k, T.xmax, T.rxmax);
