@@ -290,6 +290,10 @@ def secondary_probes(torch, P, tables, peak, scale=1.0):
     rec["hbm_frac_main_kernel"] = (ALGO_BYTES_PER_PARTICLE_STEP * rk["kern_rows"] / (rk["kern_ms"] * 1e-3) / 1e9 / peak) if rk["kern_ms"] > 0 else None
     rec["ms_per_step_species_in_sequence"] = rk["ms"] / 3
     rec["kernel_timing"] = "streaming kernel timed with the species of a pass launched in sequence; ms_per_step with the default overlap"
+    # the kernel does not rewrite the columns a free flight leaves unchanged (p, w, r): it moves 110.6 B per row (ncu,
+    # profiles/r2_photon_stream_kernel_ncu_summary.csv), not the 162 algorithmic bytes, so the algorithmic fraction can exceed 1
+    rec["dram_bytes_per_row_ncu"] = 110.6
+    rec["hbm_frac_main_kernel_by_traffic"] = (110.6 * rk["kern_rows"] / (rk["kern_ms"] * 1e-3) / 1e9 / peak) if rk["kern_ms"] > 0 else None
     out["photon_streaming"] = rec
     ctx.close()
     # (2) electrons at kappa ~ 1 (dt scaled down): where HBM binds for leptons
@@ -352,27 +356,38 @@ def strong_leg(torch, dist, P, ctx, mp, el, psh, args, rank, world, barrier):
     column_tensor(torch, el, 7, n).fill_(t)
     steps, warmup = max(args.steps, 1), max(args.warmup, 1)
     coll_ms = 0.0
+    diag_ms = 0.0
+    wait_ms = 0.0
     moved_rows = 0
     psteps = 0
 
     def one(it, timed):
-        nonlocal t, coll_ms, moved_rows, psteps
+        nonlocal t, coll_ms, diag_ms, wait_ms, moved_rows, psteps
         n0 = len(el)
         t += DT
         P.advance(mp, psh, t)
         for q in mp:
             P.droplow(q)
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
+        # what a rank spends from the end of its own step to the end of the collectives has two parts: WAITING for the slowest
+        # rank (load imbalance: it would wait at the next synchronisation point anyway) and the collectives themselves.  A
+        # barrier in front separates the two.
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        dist.barrier()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
         d = pdist.diag_allreduce(el)                      # global counts / moments every step (run.jl:31-40)
+        w2 = time.perf_counter()
         if it % 2 == 1:
             _, mv = pdist.rebalance_device(el, tolerance=0.02)
             if timed:
                 moved_rows += abs(mv)
-        c1.record()
-        torch.cuda.synchronize()
+        ctx.synchronize()
+        w3 = time.perf_counter()
         if timed:
-            coll_ms += c0.elapsed_time(c1)
+            wait_ms += (w1 - w0) * 1e3
+            diag_ms += (w2 - w1) * 1e3
+            coll_ms += (w3 - w1) * 1e3
             psteps += n0
         return d
 
@@ -386,7 +401,7 @@ def strong_leg(torch, dist, P, ctx, mp, el, psh, args, rank, world, barrier):
         d = one(warmup + it, True)
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1), coll_ms], device="cuda", dtype=torch.float64)
+    ms = torch.tensor([e0.elapsed_time(e1), coll_ms, diag_ms, wait_ms], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(psteps), float(moved_rows), float(len(el))], device="cuda", dtype=torch.float64)
     nmax = torch.tensor([float(len(el))], device="cuda", dtype=torch.float64)
     nmin = nmax.clone()
@@ -396,10 +411,14 @@ def strong_leg(torch, dist, P, ctx, mp, el, psh, args, rank, world, barrier):
     dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
     return {"scaling": "strong", "electrons_total": total, "electrons_per_gpu_start": counts, "steps": steps,
             "value": float(tot[0]) / (float(ms[0]) * 1e-3), "unit": "particle-steps/s", "ms_per_step": float(ms[0]) / steps,
-            "collective_ms_per_step": float(ms[1]) / steps, "rebalanced_rows_per_step": float(tot[1]) / 2 / steps,
+            "collective_ms_per_step": float(ms[1]) / steps, "diag_allreduce_ms_per_step": float(ms[2]) / steps,
+            "rebalance_ms_per_step": (float(ms[1]) - float(ms[2])) / steps, "wait_for_slowest_rank_ms_per_step": float(ms[3]) / steps,
+            "rebalanced_rows_per_step": float(tot[1]) / 2 / steps,
             "global_n_from_diag_allreduce": int(d.n), "global_n_from_sum": int(tot[2]),
             "n_per_gpu_end": {"max": int(nmax.item()), "min": int(nmin.item())},
-            "collectives": "ptl_diag_allreduce every step + ptl_rebalance (tolerance 2 %) every second step, NCCL called from the library, inside the timed region"}
+            "collectives": "ptl_diag_allreduce every step + ptl_rebalance (tolerance 2 %) every second step, NCCL called from the library, inside the timed "
+                           "region; *_ms_per_step are host wall times, max over ranks; a barrier in front of the collectives separates waiting for the slowest "
+                           "rank (load imbalance) from the collectives themselves"}
 
 
 def main():

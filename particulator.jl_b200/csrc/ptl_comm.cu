@@ -118,6 +118,20 @@ EXPORT int32_t ptl_comm_init(ptl_context* ctx, const uint8_t* id, int32_t rank, 
     NK(CommInitRank(&comm, nranks, uid, rank));
     ctx->comm = comm; ctx->rank = rank; ctx->nranks = nranks;
     if (!ctx->d_coll) CK(cudaMalloc(&ctx->d_coll, sizeof(double) * PTL_COLL_SCRATCH));
+    // NCCL sets up point-to-point connections lazily, at the first send / recv between a pair (tens of ms each): a
+    // rebalance that pairs two ranks for the first time would pay that inside a time step.  Connect every pair now with
+    // one grouped exchange of a single element per peer (measured on 8 B200: 43 ms -> see DESIGN.md section 7 per step).
+    if (nranks > 1 && nranks <= PTL_COLL_SCRATCH / 2) {
+        NK(GroupStart());
+        for (int peer = 0; peer < nranks; peer++) {
+            if (peer == rank) continue;
+            NK(Send(ctx->d_coll + peer, 1, ncclDouble, peer, comm, ctx->stream));
+            NK(Recv(ctx->d_coll + nranks + peer, 1, ncclDouble, peer, comm, ctx->stream));
+        }
+        NK(GroupEnd());
+        NK(AllReduce(ctx->d_coll, ctx->d_coll, 1, ncclDouble, ncclSum, comm, ctx->stream));      // and the collective channels
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     // default uids of this context never collide with another rank's (every context used to start at 1)
     if (ctx->next_uid < ((uint64_t)rank << 40) + 1) ctx->next_uid = ((uint64_t)rank << 40) + 1;
     return 0;
