@@ -438,6 +438,9 @@ def main():
     ap.add_argument("--strong-total", type=int, default=int(os.environ.get("PTL_BENCH_STRONG_TOTAL", 100_000_000)))
     ap.add_argument("--secondary-scale", type=float, default=1.0, help="scale the secondary probe populations (tests use < 1)")
     ap.add_argument("--e2e-shards", type=int, default=int(os.environ.get("PTL_E2E_SHARDS", 12)))
+    ap.add_argument("--e2e-ramp", type=float, default=float(os.environ.get("PTL_E2E_RAMP", 0.3)),
+                    help="relative size of the first and last shard of the e2e leg (1 = equal shards): small shards at both ends shorten "
+                         "the time before the first kernel can start and the last download after the last kernel")
     ap.add_argument("--e2e-workers", type=int, default=int(os.environ.get("PTL_E2E_WORKERS", 3)))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -599,8 +602,18 @@ def main():
         # their own library contexts: while one context advances a shard, the other one's H2D / D2H copies run on the
         # copy engines.  Every byte still crosses PCIe inside the timed region.
         nshards, nworkers = max(args.e2e_shards, 1), max(args.e2e_workers, 1)
-        bounds = [n_e2e * k // nshards for k in range(nshards + 1)]
-        shard_cap = int(1.7 * (bounds[1] - bounds[0])) + 8192
+        # shard sizes ramp up over the first `nworkers` shards and down over the last ones (pipeline fill / drain): nothing can
+        # overlap the upload of the very first shard or the download of the very last one, so those are kept small
+        wts = [1.0] * nshards
+        if nshards >= 3 * nworkers and 0 < args.e2e_ramp < 1:
+            for k in range(nworkers):
+                f = args.e2e_ramp + (1 - args.e2e_ramp) * k / nworkers
+                wts[k] = f
+                wts[nshards - 1 - k] = f
+        cum = np.concatenate([[0.0], np.cumsum(wts)]) / sum(wts)
+        bounds = [int(round(n_e2e * c)) for c in cum]
+        bounds[0], bounds[-1] = 0, n_e2e
+        shard_cap = int(1.7 * max(bounds[k + 1] - bounds[k] for k in range(nshards))) + 8192
         workers = []
         for wk in range(nworkers):
             wctx = P.Context(device=local_rank)                       # own non-blocking stream
@@ -674,7 +687,7 @@ def main():
                "h2d_bytes_per_step": 89 * n_e2e, "d2h_bytes_per_step": 89 * d2h_rows // max(args.e2e_steps, 1), "steps": args.e2e_steps,
                "ms_per_step": float(e2e_ms.item()) / max(args.e2e_steps, 1),
                "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download, "
-                       f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other)",
+                       f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other; first/last shards {args.e2e_ramp:g}x the middle ones)",
                "timer": "host wall clock between device-wide synchronizes (work spans several streams)",
                "worker_phase_ms_last_step": {"upload": [round(p[0], 1) for p in phase_ms], "advance_droplow": [round(p[1], 1) for p in phase_ms],
                                              "download": [round(p[2], 1) for p in phase_ms]}}

@@ -196,7 +196,7 @@ int32_t  ptl_set_uid_counter(ptl_context* ctx, uint64_t next_uid);
 uint64_t ptl_get_uid_counter(ptl_context* ctx);
 /* Tuning knobs outside the reference's surface: "kernel" = lepton advance kernel variant (0 default,
  * 3 list-scheduled, 4 re-sorting, 5 warp-private pools; all give identical results), "stream" = 0/1
- * streaming fast path for low-kappa species, "small_pass_rows" = lepton passes with fewer rows than this run
+ * streaming fast path for low-kappa species, "stream_tma" = 0/1 TMA-staged streaming kernel for leptons, "small_pass_rows" = lepton passes with fewer rows than this run
  * on the one-particle-per-lane kernel (latency regime; 0 = always the wavefront kernel), "overlap" = 0/1 run the
  * species of one pass of advance1! concurrently on forked streams (they are independent of each other). */
 int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value);

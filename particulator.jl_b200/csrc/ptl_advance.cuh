@@ -71,6 +71,25 @@ static __device__ __noinline__ double setr(const AdvanceParams& P, const SmemTab
     return own_ratebound<SP>(P, S, eng);
 }
 
+// setr! for the common table shape (Chebyshev, order 3), inline on the shared-memory rate-bound rows: ~55 instructions.
+// The generic setr<SP> is an out-of-line call that reads AdvanceParams through a generic pointer and carries the
+// any-order loop and the IEEE-division fallback (112 executed instructions per call, 6 % of the kernel in ncu).
+// (Measured: as a real function, -DPTL_SETR3_NOINLINE, 29.7 ms against 27.6 ms inline for the main pass of 4e6 electrons.)
+template <int SP>
+#ifdef PTL_SETR3_NOINLINE
+__device__ __noinline__ double wf_setr_cheb3(
+#else
+__device__ __forceinline__ double wf_setr_cheb3(
+#endif
+const AdvanceParams& P, const TableView& T, const double* __restrict__ rb, double cut, Vec3 p) {
+    const double eng = kinenergy<SP>(p);
+    if (eng < cut) return 0.0;                                                         // collisions.jl:66
+    const Pre pre = precheb(eng, T.k, T.xmax, T.rxmax);
+    if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
+    const double* a = rb + 3 * pre.i;
+    return __dadd_rn(__dadd_rn(a[0], __dmul_rn(a[1], pre.a)), __dmul_rn(a[2], pre.b));   // chebsum, order 3
+}
+
 // Repeated below-cut sub-steps taken in blocks (used by every advance kernel; see the comment in ptl_advance_wf.cuh).
 // A particle that the field decelerated below energy_cut keeps its old r != 0: do_one_collision! returns before it draws
 // anything (collisions.jl:148-151), so the loop of mixed_population.jl:66-87 repeats the same dt = s/r push until tfinal or
@@ -303,6 +322,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_ad
     }
     __syncthreads();
     unsigned long long nsub = 0;
+    const bool cheb3 = T.kind == 0 && T.order == 3;     // the usual table shape: setr! inline on the shared-memory rate bound (~55 instructions)
+    const double cut = Q.energy_cut;
     constexpr int NP = (SP == PTL_PHOTON) ? 2 : 1;      // particles per thread
     const long long npairs = (i1 - i0 + NP - 1) / NP;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < npairs; q += (long long)gridDim.x * blockDim.x) {
@@ -335,7 +356,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_ad
             Vec3 p = {h ? c[3].y : c[3].x, h ? c[4].y : c[4].x, h ? c[5].y : c[5].x};
             double t = h ? c[6].y : c[6].x, s = h ? c[7].y : c[7].x, r0 = h ? c[8].y : c[8].x;
             if (!act) continue;
-            double r = FIRST ? setr<SP>(P, S, p) : r0;           // advance_init!
+            double r = FIRST ? (cheb3 ? wf_setr_cheb3<SP>(P, T, S.ratebound, cut, p) : setr<SP>(P, S, p)) : r0;           // advance_init!
             double trem = P.tfinal - t;
             if (!(trem > DBL_EPS)) {                              // nothing to do this step (:66)
                 if (FIRST && r != r0) { wr_r[h] = true; rs[h] = r; }
@@ -377,6 +398,135 @@ __global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_ad
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) if (wr_r[h]) Q.col[COL_R][i + h] = rs[h];
+    }
+    for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
+    if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(P.substeps + SP, nsub);
+}
+
+// K1t: the streaming fast path for LEPTONS with the rows staged through shared memory by the TMA engine.
+// k_advance_stream<lepton> (one row per thread, plain loads) reaches 54 % of the measured HBM bandwidth at kappa ~ 1
+// (profiles/r2_electron_stream_kernel_ncu_summary.csv): 24 resident warps per SM each issue ten loads and then spend ~400
+// instructions on setr! and the RK2 push before they ask for memory again — long-scoreboard stall 12.9 warps per issue, the
+// memory system idles while the warps compute.  Here the loads do not belong to the warps: a persistent CTA walks over tiles
+// of STT_ROWS rows; one thread arms an mbarrier and issues ten bulk copies (cp.async.bulk, nine double columns + the
+// active bytes) per tile into a ring of STT_STAGES shared-memory stages, STT_STAGES - 1 tiles ahead of the one being
+// computed, so ~50 KB per CTA are in flight whatever the warps are doing.  Results go back with plain coalesced stores
+// (fire and forget).  Same arithmetic, same deferral of rows that collide within dt as k_advance_stream.
+constexpr int STT_ROWS = 256;            // rows per tile = threads per CTA
+constexpr int STT_STAGES = 3;
+constexpr int STT_STAGE_BYTES = 9 * STT_ROWS * 8 + STT_ROWS;     // nine double columns + active bytes
+constexpr size_t STT_RING_BYTES = (size_t)STT_STAGES * STT_STAGE_BYTES + 8 * STT_STAGES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int SP, bool FIRST>
+__global__ void __launch_bounds__(STT_ROWS, 3) k_advance_stream_tma(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                                    long long* __restrict__ slow_rows, unsigned long long* slow_count) {
+    extern __shared__ __align__(128) unsigned char stt_smem[];
+    const TableView& T = P.tab[SP];
+    const PopView& Q = P.pop[SP];
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stt_smem + (size_t)STT_STAGES * STT_STAGE_BYTES);
+    double* rbs = reinterpret_cast<double*>(stt_smem + STT_RING_BYTES);
+    SmemTable S;
+    S.rate = nullptr; S.procs = nullptr;
+    if (T.kind == 0) {
+        const int nrb = T.order * (T.k + 1);
+        for (int q = threadIdx.x; q < nrb; q += blockDim.x) rbs[q] = T.ratebound[q];
+        S.ratebound = rbs;
+    } else {
+        S.ratebound = nullptr;
+    }
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < STT_STAGES; st++) mbar_init(smem_u32(bars + st), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const bool cheb3 = T.kind == 0 && T.order == 3;
+    const double cut = Q.energy_cut;
+    const long long ntiles = (i1 - i0 + STT_ROWS - 1) / STT_ROWS;
+    // i0 is a multiple of 16 (launcher), so every tile starts on a 16-byte boundary of every column, the byte column included
+    auto issue = [&](long long tile, int st) {
+        const long long r0 = i0 + tile * STT_ROWS;
+        long long nr = i1 - r0;
+        if (nr > STT_ROWS) nr = STT_ROWS;
+        const uint32_t nb8 = (uint32_t)((nr + 1) & ~1LL) * 8u;          // bulk copies move multiples of 16 bytes: the padding of a
+        const uint32_t nb1 = (uint32_t)((nr + 15) & ~15LL);             // partial last tile lies inside the 256-byte aligned column
+        const uint32_t bar = smem_u32(bars + st);
+        unsigned char* base = stt_smem + (size_t)st * STT_STAGE_BYTES;
+        mbar_expect_tx(bar, 9u * nb8 + nb1);
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            const int col = k < 6 ? k : k + 1;                          // x0..p2, t, s, r  (w is not needed)
+            bulk_g2s(smem_u32(base + (size_t)k * STT_ROWS * 8), Q.col[col] + r0, nb8, bar);
+        }
+        bulk_g2s(smem_u32(base + 9 * STT_ROWS * 8), Q.active + r0, nb1, bar);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int st = 0; st < STT_STAGES - 1; st++) {
+            const long long tile = blockIdx.x + (long long)st * gridDim.x;
+            if (tile < ntiles) issue(tile, st);
+        }
+    }
+    unsigned long long nsub = 0;
+    int st = 0;
+    uint32_t parity = 0;
+    for (long long tile = blockIdx.x, k = 0; tile < ntiles; tile += gridDim.x, k++) {
+        if (threadIdx.x == 0) {       // refill the stage the CTA finished reading at the end of the previous iteration
+            const long long ahead = tile + (long long)(STT_STAGES - 1) * gridDim.x;
+            if (ahead < ntiles) issue(ahead, (st + STT_STAGES - 1) % STT_STAGES);
+        }
+        mbar_wait(smem_u32(bars + st), parity);
+        const unsigned char* base = stt_smem + (size_t)st * STT_STAGE_BYTES;
+        const double* cd = reinterpret_cast<const double*>(base);
+        const long long i = i0 + tile * STT_ROWS + threadIdx.x;
+        if (i < i1 && base[9 * STT_ROWS * 8 + threadIdx.x] != 0) {
+            const int q = threadIdx.x;
+            Vec3 x = {cd[q], cd[STT_ROWS + q], cd[2 * STT_ROWS + q]};
+            Vec3 p = {cd[3 * STT_ROWS + q], cd[4 * STT_ROWS + q], cd[5 * STT_ROWS + q]};
+            double t = cd[6 * STT_ROWS + q], s = cd[7 * STT_ROWS + q];
+            const double r0 = cd[8 * STT_ROWS + q];
+            const double r = FIRST ? (cheb3 ? wf_setr_cheb3<SP>(P, T, S.ratebound, cut, p) : setr<SP>(P, S, p)) : r0;          // advance_init!
+            const double trem = P.tfinal - t;
+            if (!(trem > DBL_EPS)) {                                  // nothing to do this step (:66)
+                if (FIRST && r != r0) Q.col[COL_R][i] = r;
+            } else if (trem > s / r) {                                // collides within dt: defer to the general kernel
+                unsigned long long kk = atomicAdd(slow_count, 1ULL);
+                slow_rows[kk] = i;
+            } else {
+                s -= trem * r;                                        // :74
+                push<SP>(P, x, p, t, trem);                           // :77
+                nsub++;
+                Q.col[COL_X0][i] = x.x; Q.col[COL_X1][i] = x.y; Q.col[COL_X2][i] = x.z;
+                Q.col[COL_P0][i] = p.x; Q.col[COL_P1][i] = p.y; Q.col[COL_P2][i] = p.z;
+                Q.col[COL_T][i] = t; Q.col[COL_S][i] = s;
+                if (FIRST && r != r0) Q.col[COL_R][i] = r;
+            }
+        }
+        __syncthreads();              // every thread has read its row: the stage may be overwritten by the next bulk copies
+        if (++st == STT_STAGES) { st = 0; parity ^= 1u; }
     }
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);
     if ((threadIdx.x & 31) == 0 && nsub) atomicAdd(P.substeps + SP, nsub);

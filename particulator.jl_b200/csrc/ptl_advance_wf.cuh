@@ -36,6 +36,9 @@ constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the s
 #ifndef WF_RBEB_TRIALS
 #define WF_RBEB_TRIALS 0                 // rejection trials evaluated side by side per RBEB unit (0: the sequential two-trial loop)
 #endif
+#ifndef WF_RBEB_LOOP
+#define WF_RBEB_LOOP 5                   // sequential rejection trials per RBEB unit before the slot goes back to the scheduler (see the RBEB unit)
+#endif
 constexpr uint32_t WF_VALID = 0x100u;   // slot holds a particle that must be written back
 constexpr uint32_t WF_DEAD = 0x200u;    // ... and it was deactivated
 constexpr uint32_t WF_COAST = 0x400u;   // OTHER unit: no collision, take the repeated below-cut sub-steps in blocks
@@ -104,26 +107,7 @@ static __device__ __noinline__ unsigned long long wf_coast_below_cut(const Advan
     return nsub;
 }
 
-// after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP
-// setr! for the common table shape (Chebyshev, order 3), inline on the shared-memory rate-bound rows: ~55 instructions.
-// The generic setr<SP> is an out-of-line call that reads AdvanceParams through a generic pointer and carries the
-// any-order loop and the IEEE-division fallback (112 executed instructions per call, 6 % of the kernel in ncu).
-// (Measured: as a real function, -DPTL_SETR3_NOINLINE, 29.7 ms against 27.6 ms inline for the main pass of 4e6 electrons.)
-template <int SP>
-#ifdef PTL_SETR3_NOINLINE
-__device__ __noinline__ double wf_setr_cheb3(
-#else
-__device__ __forceinline__ double wf_setr_cheb3(
-#endif
-const AdvanceParams& P, const TableView& T, const double* __restrict__ rb, double cut, Vec3 p) {
-    const double eng = kinenergy<SP>(p);
-    if (eng < cut) return 0.0;                                                         // collisions.jl:66
-    const Pre pre = precheb(eng, T.k, T.xmax, T.rxmax);
-    if (pre.oob) atomicOr(P.flags, PTL_ERR_ENERGY_OUT_OF_TABLE);
-    const double* a = rb + 3 * pre.i;
-    return __dadd_rn(__dadd_rn(a[0], __dmul_rn(a[1], pre.a)), __dmul_rn(a[2], pre.b));   // chebsum, order 3
-}
-
+// after a real collision changed p: apply!'s setr! (collisions.jl:93,99) and back to STEP (wf_setr_cheb3: ptl_advance.cuh)
 template <int SP>
 __device__ __forceinline__ void wf_after_collision(const AdvanceParams& P, const SmemTable& T, const WfPool& S, int it, Vec3 p, double s,
                                                    const bool cheb3 = false, const double cut = 0.0) {
@@ -273,31 +257,70 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
     return jsel;
 }
 
-// One work unit of slot `it` (state word `sw`).  Shared by the barrier-synchronous kernel (k_advance_wf) and the
-// queue-driven kernel (k_advance_aq).  `ldmask` = lanes of this warp that execute a LOAD unit right now (they share one
-// atomic on the global row counter).
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+// The OTHER unit (rare processes: the whole collide() + apply!; also the block-coasting of below-cut particles) as a
+// function of its own.  Inlined it is ~2000 instructions of cold code in the middle of the kernel body, between the STEP
+// and the RBEB units.  Out of line (WQ_OTHER_OUTLINE, warp-private kernel) it takes scalars only and rebuilds the pool and
+// table views from the shared-memory base, so that no pointer has to stay live in the caller for its sake.
+template <int SP, int TK>
+__device__ __forceinline__ unsigned long long wf_other_unit(const AdvanceParams& P, const PopView& Q, const WfPool& S, const SmemTable& TS,
+                                                            const bool fastsel, const RngCtx rc, const double cut, const int it, const uint32_t sw) {
+    unsigned long long nsub = 0;
+    do {
+        if (sw & WF_COAST) {
+            nsub += wf_coast_below_cut<SP>(P, S, it, cut);
+            break;
+        }
+        Rng rng;
+        wf_load_rng(S, it, rng);
+        Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
+        double eng = kinenergy<SP>(p), t = WFD(WD_T, it);       // same p, same function as the STEP unit's test: same bits
+        Outcome o;
+        collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
+        wf_store_rng(S, it, rng);
+        long long i = S.row[it];
+        uint64_t cu[2];
+        switch (o.kind) {
+        case OUT_NULL:
+            WFD(WD_R, it) = setr<SP>(P, TS, p);
+            WFD(WD_S, it) = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
+            wf_store_rng(S, it, rng);
+            S.state[it] = WS_STEP | WF_VALID;
+            break;
+        case OUT_STATE_CHANGE:
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
+            break;
+        case OUT_NEW_PARTICLE:
+            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            break;
+        case OUT_REMOVE:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            break;
+        case OUT_REPLACE:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            break;
+        case OUT_REPLACE_PAIR:
+            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
+            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
+            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
+            add_particle(P, o.sp3, x, o.p3, Q.col[COL_W][i], t, o.s3, cu[1]);
+            break;
+        }
+    } while (0);
+    return nsub;
 }
 
-// ALOAD (warp-private kernel only): the LOAD unit does not wait for the row — it issues cp.async copies of the twelve
-// column entries straight into the slot and parks the slot in class LOADWAIT; the warp goes on with other classes while
-// HBM answers (the synchronous LOAD was the one long-scoreboard stall of the kernel: 0.55-0.7 warps per issue), and the
-// LOADWAIT unit, run after a warp-wide cp.async.wait_all, finishes advance_init! on the arrived row.
-template <int SP, int TK, bool FIRST, bool CB, bool ALOAD = false>
-__device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const TableView& T, const PopView& Q, const WfPool& S,
-                                                const SmemTable& TS, const double* tcum, const bool fastsel, const RngCtx rc,
-                                                const double cut, const int it, const uint32_t sw, const unsigned ldmask,
-                                                const int lane, const unsigned ltmask, unsigned long long* row_counter,
-                                                const long long i0, const long long i1, unsigned long long& nsub,
-                                                const long long* __restrict__ rows = nullptr) {
-    const int cls = (int)(sw & 0xffu);
-    switch (cls) {
-    // ------------------------------------------------------------------------------------------
-    case WS_LOAD: {   // write back the finished particle of this slot (if any), fetch the next row
+// The LOAD unit (write back the finished particle of a slot, fetch the next row) as a function of its own: 1 % of the
+// rounds, ~250 instructions that otherwise sit between the STEP and the RBEB units in the kernel body.
+template <int SP, int TK, bool FIRST, bool ALOAD>
+__device__ __forceinline__ void wf_load_unit(const AdvanceParams& P, const TableView& T, const PopView& Q, const WfPool& S, const SmemTable& TS,
+                                             const bool fastsel, const double cut, const int it, const uint32_t sw, const unsigned ldmask,
+                                             const int lane, const unsigned ltmask, unsigned long long* row_counter, const long long i0,
+                                             const long long i1, const long long* __restrict__ rows) {
+    do {
         if (sw & WF_VALID) {
             long long i = S.row[it];
             Q.col[COL_X0][i] = WFD(WD_X0, it); Q.col[COL_X1][i] = WFD(WD_X1, it); Q.col[COL_X2][i] = WFD(WD_X2, it);
@@ -336,6 +359,40 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         S.uid[it] = Q.uid[i]; S.row[it] = i;
         S.idx[it] = 0; S.cblock[it] = 0xFFFFFFFFu; S.c2[it] = 0; S.c3[it] = 0;
         S.state[it] = WS_STEP | WF_VALID;
+            } while (0);
+}
+
+// One work unit of slot `it` (state word `sw`).  Shared by the barrier-synchronous kernel (k_advance_wf) and the
+// queue-driven kernel (k_advance_aq).  `ldmask` = lanes of this warp that execute a LOAD unit right now (they share one
+// atomic on the global row counter).
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// ALOAD (warp-private kernel only): the LOAD unit does not wait for the row — it issues cp.async copies of the twelve
+// column entries straight into the slot and parks the slot in class LOADWAIT; the warp goes on with other classes while
+// HBM answers (the synchronous LOAD was the one long-scoreboard stall of the kernel: 0.55-0.7 warps per issue), and the
+// LOADWAIT unit, run after a warp-wide cp.async.wait_all, finishes advance_init! on the arrived row.
+template <int SP, int TK, bool FIRST, bool CB, bool ALOAD = false>
+__device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const TableView& T, const PopView& Q, const WfPool& S,
+                                                const SmemTable& TS, const double* tcum, const bool fastsel, const RngCtx rc,
+                                                const double cut, const int it, const uint32_t sw, const unsigned ldmask,
+                                                const int lane, const unsigned ltmask, unsigned long long* row_counter,
+                                                const long long i0, const long long i1, unsigned long long& nsub,
+                                                const long long* __restrict__ rows = nullptr, const int cls_uniform = -1,
+                                                unsigned long long (*other_out)(const AdvanceParams*, int, uint32_t) = nullptr,
+                                                void (*load_out)(const AdvanceParams*, int, uint32_t, unsigned, unsigned long long*, long long, long long, const long long*) = nullptr) {
+    // cls_uniform >= 0: the caller guarantees that every executing lane of the warp holds a slot of this class (the
+    // warp-private kernel), so the dispatch is a warp-uniform branch instead of a divergent switch on the state word
+    const int cls = cls_uniform >= 0 ? cls_uniform : (int)(sw & 0xffu);
+    switch (cls) {
+    // ------------------------------------------------------------------------------------------
+    case WS_LOAD: {   // write back the finished particle of this slot (if any), fetch the next row
+        if (load_out != nullptr) load_out(&P, it, sw, ldmask, row_counter, i0, i1, rows);
+        else wf_load_unit<SP, TK, FIRST, ALOAD>(P, T, Q, S, TS, fastsel, cut, it, sw, ldmask, lane, ltmask, row_counter, i0, i1, rows);
         break;
     }
     // ------------------------------------------------------------------------------------------
@@ -529,7 +586,7 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         double w;
         bool acc = false;
 #pragma unroll 1
-        for (int q = 0; q < 2 && !acc; q++) {
+        for (int q = 0; q < WF_RBEB_LOOP && !acc; q++) {
             double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
             double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
             acc = rbeb_trial(k, u, u2, w);
@@ -565,51 +622,10 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
     }
     // ------------------------------------------------------------------------------------------
     case WS_OTHER: {   // rare processes: the whole collide() + apply! in one unit
-        // (moving this unit out of line to keep the hot units' code contiguous was measured 4.6 % SLOWER: passing the pool
-        // by reference to a real function keeps its pointers live in registers across the whole kernel)
-        if (sw & WF_COAST) {
-            nsub += wf_coast_below_cut<SP>(P, S, it, cut);
-            break;
-        }
-        Rng rng;
-        wf_load_rng(S, it, rng);
-        Vec3 p = wf_get3(S, WD_P0, it), x = wf_get3(S, WD_X0, it);
-        double eng = kinenergy<SP>(p), t = WFD(WD_T, it);       // same p, same function as the STEP unit's test: same bits
-        Outcome o;
-        collide<SP>(rng, rc, P, TS.procs[sw >> 16], p, eng, o);
-        wf_store_rng(S, it, rng);
-        long long i = S.row[it];
-        uint64_t cu[2];
-        switch (o.kind) {
-        case OUT_NULL:
-            WFD(WD_R, it) = setr<SP>(P, TS, p);
-            WFD(WD_S, it) = -nlog(rng.u(rc.step, rc.seed_lo, rc.seed_hi));
-            wf_store_rng(S, it, rng);
-            S.state[it] = WS_STEP | WF_VALID;
-            break;
-        case OUT_STATE_CHANGE:
-            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
-            break;
-        case OUT_NEW_PARTICLE:
-            wf_after_collision<SP>(P, TS, S, it, o.p1, o.s1, fastsel, cut);
-            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-            break;
-        case OUT_REMOVE:
-            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-            break;
-        case OUT_REPLACE:
-            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-            break;
-        case OUT_REPLACE_PAIR:
-            S.state[it] = WS_LOAD | WF_VALID | WF_DEAD;
-            child_uids(S.uid[it], rng.idx, rc.step, rc.seed_lo, rc.seed_hi, cu);
-            add_particle(P, o.sp2, x, o.p2, Q.col[COL_W][i], t, o.s2, cu[0]);
-            add_particle(P, o.sp3, x, o.p3, Q.col[COL_W][i], t, o.s3, cu[1]);
-            break;
-        }
+        // (moving this unit out of line by passing the pool by reference to a real function was measured 4.6 % SLOWER: its
+        // pointers then stay live in registers across the whole kernel; see wf_other_unit for the version that does not)
+        if (other_out != nullptr) nsub += other_out(&P, it, sw);
+        else nsub += wf_other_unit<SP, TK>(P, Q, S, TS, fastsel, rc, cut, it, sw);
         break;
     }
     default: break;

@@ -65,6 +65,7 @@ EXPORT int32_t ptl_context_create(int32_t device, void* stream, ptl_context** ou
     if (const char* km = getenv("PTL_KERNEL")) {      // A/B measurements; ptl_set_option does the same per context
         ctx->lepton_kernel = !strcmp(km, "wq") ? 5 : (!strcmp(km, "bq") ? 3 : (!strcmp(km, "wf") ? 4 : 0));
         if (!strcmp(km, "nostream")) ctx->use_stream = false;
+        if (!strcmp(km, "tma")) ctx->use_stream_tma = true;
     }
     if (const char* sp = getenv("PTL_SMALL_PASS")) ctx->small_pass_rows = atoll(sp);
     if (const char* ov = getenv("PTL_OVERLAP")) ctx->overlap_species = atoi(ov) != 0;
@@ -152,6 +153,7 @@ EXPORT int32_t ptl_set_option(ptl_context* ctx, const char* name, int64_t value)
         return 0;
     }
     if (!strcmp(name, "stream")) { ctx->use_stream = value != 0; return 0; }
+    if (!strcmp(name, "stream_tma")) { ctx->use_stream_tma = value != 0; return 0; }
     if (!strcmp(name, "overlap")) { ctx->overlap_species = value != 0; return 0; }
     if (!strcmp(name, "small_pass_rows")) { if (value < 0) return PTL_EINVAL; ctx->small_pass_rows = value; return 0; }
     ctx->err = std::string("unknown option ") + name;

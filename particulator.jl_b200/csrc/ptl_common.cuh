@@ -10,6 +10,18 @@
 #include <cuda_runtime.h>
 #include "../../include/particulator_b200.h"
 
+// Code placement.  ptxas lays the out-of-line device functions of a kernel out behind its body in the order of their
+// mangled names.  -DPTL_HOT_NAMES renames the four functions the hot work units call so that they sort first, i.e. sit
+// right behind the kernel body instead of up to 150 KB away from it (instruction-cache experiment).
+#ifdef PTL_HOT_NAMES
+#define philox_block a_hot_phlx
+#define nlog a_hot_nlog
+#define nsincospi a_hot_scpi
+#if PTL_HOT_NAMES > 1      // (add_particle is 615 instructions and only runs for births above the cut: it is NOT hot; =2 reproduces the first measurement)
+#define add_particle a_hot_addp
+#endif
+#endif
+
 namespace ptl {
 
 // ---- constants: reference src/constants.jl (CODATA-2014), same expression order ----------------

@@ -106,6 +106,7 @@ struct ptl_context {
     int lepton_kernel = 0;             // 0 = default (PTL_DEFAULT_LEPTON_KERNEL), 3 = bq, 4 = wf, 5 = wq (ptl_set_option "kernel" / PTL_KERNEL)
     long long small_pass_rows = 16384; // lepton passes with fewer rows run on the one-particle-per-lane kernel (chain latency, not throughput)
     bool use_stream = true;            // streaming fast path for low-kappa species (ptl_set_option "stream" / PTL_KERNEL=nostream)
+    bool use_stream_tma = false;       // leptons on the streaming path: TMA-staged kernel (ptl_set_option "stream_tma" / PTL_KERNEL=tma); measured slower, off
     long long launch_total = 0;        // kernels launched since the last ptl_launch_count(reset)
     bool profiling = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -11,6 +11,11 @@
 #define PTL_DEFAULT_LEPTON_KERNEL 5     // 3 = bq (list-scheduled, round 1), 5 = wq (warp-private pools, round 2)
 #endif
 
+#ifndef WQ_USE_FS
+#define WQ_USE_FS 0                     // 1: tables of the usual shape run a kernel with the fast selection compiled in (template parameter FS);
+                                        // measured 9 % SLOWER (27.6 against 25.3 ms): fewer instructions, but the layout ptxas then picks misses more in the instruction cache
+#endif
+
 namespace ptl_host {
 
 template <int SP, bool FIRST, bool CB>
@@ -101,9 +106,9 @@ int32_t launch_advance_bq_k(ptl_context* ctx, const AdvanceParams& A, long long 
 }
 
 // warp-private variant (round 2): every warp owns WQ_NS slots; no CTA barrier, no shared lists
-template <int SP, int TK, bool FIRST, bool CB>
+template <int SP, int TK, bool FIRST, bool CB, int FS = 0>
 int32_t launch_advance_wq_k(ptl_context* ctx, const AdvanceParams& A, long long i0, long long i1, const long long* rows) {
-    auto kern = k_advance_wq<SP, TK, FIRST, CB>;
+    auto kern = k_advance_wq<SP, TK, FIRST, CB, FS>;
     const TableView& TV = A.tab[SP];
     size_t tsm = sizeof(ptl_process_desc) * TV.nprocs;
     if (TV.kind == 0) tsm += sizeof(double) * ((size_t)((TV.order == 3 && TV.nprocs <= 16) ? WF_CUM_STRIDE : TV.order * TV.nprocs) * (TV.k + 1) + (size_t)TV.order * (TV.k + 1));
@@ -135,7 +140,11 @@ int32_t launch_advance_wf_t(ptl_context* ctx, const AdvanceParams& A, long long 
     // — kept for A/B measurements and run against each other by the parity tests.
     const int variant = ctx->lepton_kernel ? ctx->lepton_kernel : PTL_DEFAULT_LEPTON_KERNEL;
     if (variant == 5) {
-        if (A.tab[SP].kind == 0) return launch_advance_wq_k<SP, 0, FIRST, CB>(ctx, A, i0, i1, rows);
+        if (A.tab[SP].kind == 0) {
+            // the usual table shape (Chebyshev, order 3, <= 16 processes) gets a kernel with the fast selection compiled in
+            if (WQ_USE_FS && A.tab[SP].order == 3 && A.tab[SP].nprocs <= 16) return launch_advance_wq_k<SP, 0, FIRST, CB, WQ_USE_FS>(ctx, A, i0, i1, rows);
+            return launch_advance_wq_k<SP, 0, FIRST, CB, 0>(ctx, A, i0, i1, rows);
+        }
         return launch_advance_wq_k<SP, 1, FIRST, CB>(ctx, A, i0, i1, rows);
     }
     if (variant != 4) {
@@ -174,7 +183,25 @@ int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0,
         if (grid > maxgrid) grid = maxgrid;
         bool timed = ctx->profiling && (i1 - i0) > ctx->stats.main_rows;
         if (timed) { ctx->stats.main_rows = i1 - i0; cudaEventRecord(ctx->ev0, ctx->lstream); }
-        if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+        bool tma = false;
+        if constexpr (SP != PTL_PHOTON) {
+            // leptons: rows staged through shared memory by bulk copies (k_advance_stream_tma); needs 16-byte aligned tiles
+            // of the byte column too, i.e. a pass that starts on a multiple of 16 rows (the first pass always does)
+            tma = ctx->use_stream_tma && (i0 & 15) == 0;
+            if (tma) {
+                const size_t tsm = STT_RING_BYTES + ssm;
+                auto k1 = k_advance_stream_tma<SP, true>;
+                auto k0 = k_advance_stream_tma<SP, false>;
+                cudaFuncSetAttribute(first ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);   // per device, see launch_advance_t
+                long long tiles = (i1 - i0 + STT_ROWS - 1) / STT_ROWS;
+                long long tg = (long long)ctx->sm_count * 3;
+                if (tg > tiles) tg = tiles;
+                if (first) k1<<<(unsigned)tg, STT_ROWS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+                else k0<<<(unsigned)tg, STT_ROWS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+            }
+        }
+        if (tma) {
+        } else if (first) k_advance_stream<SP, true><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
         else k_advance_stream<SP, false><<<(unsigned)grid, STREAM_THREADS, ssm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
         if (timed) { cudaEventRecord(ctx->ev1, ctx->lstream); ctx->ev_pending = true; }
         LAUNCHED();

@@ -287,6 +287,37 @@ def test_below_cut_coasting_matches_substep_loop(gctx, octx, air_tables):
     assert 0.2 < below.mean() < 0.999                   # both outcomes are present: still below, and back above the cut
 
 
+def test_lepton_streaming_path_replay(gctx, octx, air_tables):
+    """Leptons at kappa ~ 1 (dt scaled down 2048x): from the second advance! on the library routes the species through the
+    streaming kernels (TMA-staged k_advance_stream_tma by default, k_advance_stream with the option off) and defers only the
+    rows that collide within dt.  Both must replay the oracle particle by particle and agree with each other bit for bit;
+    6001 rows: a ragged last tile (not a multiple of the 256-row tile nor of the 16-byte copy granule)."""
+    dt = DT / 2048
+    results = []
+    for tma in (1, 0):
+        gctx.set_option("stream_tma", tma)
+        worlds = []
+        for ctx in (gctx, octx) if tma else (gctx,):
+            ctx.set_rng(11, 0)
+            worlds.append(make_world(ctx, air_tables, 6001, 0, 0, cap=20000, seed=21))
+        psh = default_pusher()
+        t = 0.0
+        for step in range(4):
+            t += dt
+            for mp, *_ in worlds:
+                P.advance(mp, psh, t)
+            if tma:
+                sg, so = P.last_advance_stats(worlds[0][0]), P.last_advance_stats(worlds[1][0])
+                assert sg["substeps"] == so["substeps"], (step, sg, so)
+                assert so["substeps"] < 1.5 * 6001              # the case really is kappa ~ 1
+                _compare_populations(worlds[0][1], worlds[1][1], f"streaming electrons step {step}")
+        results.append(_by_uid(worlds[0][1]))
+    gctx.set_option("stream_tma", 1)
+    for k in results[0]:
+        assert np.array_equal(results[0][k], results[1][k]), k     # the two streaming kernels: identical bits
+    assert gctx.error_flags(clear=True) == 0
+
+
 def test_photon_free_flight_and_time(gctx, air_tables):
     """Photons (kappa ~ 1e-4): x advances by c*dt along p, t == tfinal, p untouched for non-colliding ones."""
     mp, el, ph, po = make_world(gctx, air_tables, 0, 200000, 0, cap=300000, seed=9)
