@@ -298,6 +298,11 @@ __global__ void __launch_bounds__(ADV_THREADS) k_advance(const __grid_constant__
 // (x, t, s; r when advance_init! changed it).  Particles that do collide within dt (~1 %) are left untouched and
 // appended to an index list which the general kernel processes afterwards.
 constexpr int STREAM_THREADS = 256;
+#ifndef STREAM_LEPTON_MINB
+#define STREAM_LEPTON_MINB 2              // resident CTAs per SM the lepton streaming kernel is compiled for (register budget 65536 / 256 / this).
+                                          // Measured on B200, 1e7 electrons at kappa ~ 1: 2 CTAs (128 registers, no spills) 0.385 ms = 64 % of the measured
+                                          // HBM bandwidth; 3 CTAs (80 registers, 18 % of the instructions are spill traffic) 0.461 ms = 54 %; 4 CTAs 0.514 ms
+#endif
 
 template <int SP, bool FIRST>
 // (No minimum-blocks bound on purpose: ptxas picks 118 registers, 2 CTAs per SM, 0.39 ms for 2e7 photons = 87 % of the
@@ -306,7 +311,7 @@ template <int SP, bool FIRST>
 // registers, ONE 256-thread CTA per SM, and the kernel could not cover the HBM latency (48 % of the measured bandwidth at
 // kappa ~ 1).  They go one particle per thread (STREAM_NP = 1: 64-bit accesses, still one full 256-byte span per warp and
 // column) at three CTAs per SM; photons keep two per thread and 128-bit accesses.
-__global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+__global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : STREAM_LEPTON_MINB) k_advance_stream(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
                                                                   long long* __restrict__ slow_rows, unsigned long long* slow_count) {
     extern __shared__ double smem[];
     const TableView& T = P.tab[SP];
@@ -408,14 +413,20 @@ __global__ void __launch_bounds__(STREAM_THREADS, SP == PTL_PHOTON ? 0 : 3) k_ad
 // (profiles/r2_electron_stream_kernel_ncu_summary.csv): 24 resident warps per SM each issue ten loads and then spend ~400
 // instructions on setr! and the RK2 push before they ask for memory again — long-scoreboard stall 12.9 warps per issue, the
 // memory system idles while the warps compute.  Here the loads do not belong to the warps: a persistent CTA walks over tiles
-// of STT_ROWS rows; one thread arms an mbarrier and issues ten bulk copies (cp.async.bulk, nine double columns + the
+// of STT_ROWS rows; a producer warp arms an mbarrier and issues ten bulk copies (cp.async.bulk, nine double columns + the
 // active bytes) per tile into a ring of STT_STAGES shared-memory stages, STT_STAGES - 1 tiles ahead of the one being
 // computed, so ~50 KB per CTA are in flight whatever the warps are doing.  Results go back with plain coalesced stores
 // (fire and forget).  Same arithmetic, same deferral of rows that collide within dt as k_advance_stream.
 constexpr int STT_ROWS = 256;            // rows per tile = threads per CTA
-constexpr int STT_STAGES = 3;
+#ifndef STT_STAGES_MACRO
+#define STT_STAGES_MACRO 4
+#endif
+#ifndef STT_MINB
+#define STT_MINB 2                        // resident CTAs per SM (3 CTAs = 72 registers: ncu showed the spills missing the small L1 that 170 KB of shared memory leave)
+#endif
+constexpr int STT_STAGES = STT_STAGES_MACRO;
 constexpr int STT_STAGE_BYTES = 9 * STT_ROWS * 8 + STT_ROWS;     // nine double columns + active bytes
-constexpr size_t STT_RING_BYTES = (size_t)STT_STAGES * STT_STAGE_BYTES + 8 * STT_STAGES;
+constexpr size_t STT_RING_BYTES = (size_t)STT_STAGES * STT_STAGE_BYTES + 16 * STT_STAGES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -440,13 +451,23 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// STT_ROWS consumer threads (one row each per tile) + one producer warp.  Two mbarriers per stage: `full` (the producer's
+// expect_tx arrival + the bytes of the ten bulk copies) and `empty` (one arrival per consumer warp once its 32 rows are
+// read), so no CTA-wide barrier: a consumer warp that finds its next tile landed goes on at once.  (The first version
+// refilled from thread 0 behind a __syncthreads per tile and was slower than the plain kernel: 0.53 against 0.45 ms for
+// 1e7 electrons — every warp waited for the slowest row of the tile.)
+constexpr int STT_THREADS = STT_ROWS + 32;
 template <int SP, bool FIRST>
-__global__ void __launch_bounds__(STT_ROWS, 3) k_advance_stream_tma(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
-                                                                    long long* __restrict__ slow_rows, unsigned long long* slow_count) {
+__global__ void __launch_bounds__(STT_THREADS, STT_MINB) k_advance_stream_tma(const __grid_constant__ AdvanceParams P, long long i0, long long i1,
+                                                                      long long* __restrict__ slow_rows, unsigned long long* slow_count) {
     extern __shared__ __align__(128) unsigned char stt_smem[];
     const TableView& T = P.tab[SP];
     const PopView& Q = P.pop[SP];
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stt_smem + (size_t)STT_STAGES * STT_STAGE_BYTES);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stt_smem + (size_t)STT_STAGES * STT_STAGE_BYTES);   // full[S], empty[S]
     double* rbs = reinterpret_cast<double*>(stt_smem + STT_RING_BYTES);
     SmemTable S;
     S.rate = nullptr; S.procs = nullptr;
@@ -458,7 +479,7 @@ __global__ void __launch_bounds__(STT_ROWS, 3) k_advance_stream_tma(const __grid
         S.ratebound = nullptr;
     }
     if (threadIdx.x == 0) {
-        for (int st = 0; st < STT_STAGES; st++) mbar_init(smem_u32(bars + st), 1);
+        for (int st = 0; st < STT_STAGES; st++) { mbar_init(smem_u32(bars + st), 1); mbar_init(smem_u32(bars + STT_STAGES + st), STT_ROWS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -466,48 +487,52 @@ __global__ void __launch_bounds__(STT_ROWS, 3) k_advance_stream_tma(const __grid
     const bool cheb3 = T.kind == 0 && T.order == 3;
     const double cut = Q.energy_cut;
     const long long ntiles = (i1 - i0 + STT_ROWS - 1) / STT_ROWS;
-    // i0 is a multiple of 16 (launcher), so every tile starts on a 16-byte boundary of every column, the byte column included
-    auto issue = [&](long long tile, int st) {
-        const long long r0 = i0 + tile * STT_ROWS;
-        long long nr = i1 - r0;
-        if (nr > STT_ROWS) nr = STT_ROWS;
-        const uint32_t nb8 = (uint32_t)((nr + 1) & ~1LL) * 8u;          // bulk copies move multiples of 16 bytes: the padding of a
-        const uint32_t nb1 = (uint32_t)((nr + 15) & ~15LL);             // partial last tile lies inside the 256-byte aligned column
-        const uint32_t bar = smem_u32(bars + st);
-        unsigned char* base = stt_smem + (size_t)st * STT_STAGE_BYTES;
-        mbar_expect_tx(bar, 9u * nb8 + nb1);
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            const int col = k < 6 ? k : k + 1;                          // x0..p2, t, s, r  (w is not needed)
-            bulk_g2s(smem_u32(base + (size_t)k * STT_ROWS * 8), Q.col[col] + r0, nb8, bar);
-        }
-        bulk_g2s(smem_u32(base + 9 * STT_ROWS * 8), Q.active + r0, nb1, bar);
-    };
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int st = 0; st < STT_STAGES - 1; st++) {
-            const long long tile = blockIdx.x + (long long)st * gridDim.x;
-            if (tile < ntiles) issue(tile, st);
-        }
-    }
     unsigned long long nsub = 0;
+    if (threadIdx.x >= STT_ROWS) {
+        // ---- producer warp: one lane walks over this CTA's tiles and keeps the ring full ----
+        if (threadIdx.x == STT_ROWS) {
+            int st = 0;
+            uint32_t parity = 1;        // parity of the `empty` phase to wait for; the first pass over the ring waits for nothing
+            bool wrapped = false;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (wrapped) mbar_wait(smem_u32(bars + STT_STAGES + st), parity);
+                // i0 is a multiple of 16 (launcher): every tile starts on a 16-byte boundary of every column, the byte column included
+                const long long r0 = i0 + tile * STT_ROWS;
+                long long nr = i1 - r0;
+                if (nr > STT_ROWS) nr = STT_ROWS;
+                const uint32_t nb8 = (uint32_t)((nr + 1) & ~1LL) * 8u;      // bulk copies move multiples of 16 bytes: the padding of a
+                const uint32_t nb1 = (uint32_t)((nr + 15) & ~15LL);         // partial last tile lies inside the 256-byte aligned column
+                const uint32_t bar = smem_u32(bars + st);
+                unsigned char* base = stt_smem + (size_t)st * STT_STAGE_BYTES;
+                mbar_expect_tx(bar, 9u * nb8 + nb1);
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const int col = k < 6 ? k : k + 1;                      // x0..p2, t, s, r  (w is not needed)
+                    bulk_g2s(smem_u32(base + (size_t)k * STT_ROWS * 8), Q.col[col] + r0, nb8, bar);
+                }
+                bulk_g2s(smem_u32(base + 9 * STT_ROWS * 8), Q.active + r0, nb1, bar);
+                if (++st == STT_STAGES) { st = 0; parity = wrapped ? (parity ^ 1u) : 0u; wrapped = true; }
+            }
+        }
+        return;
+    }
+    // ---- consumer warps ----
     int st = 0;
     uint32_t parity = 0;
-    for (long long tile = blockIdx.x, k = 0; tile < ntiles; tile += gridDim.x, k++) {
-        if (threadIdx.x == 0) {       // refill the stage the CTA finished reading at the end of the previous iteration
-            const long long ahead = tile + (long long)(STT_STAGES - 1) * gridDim.x;
-            if (ahead < ntiles) issue(ahead, (st + STT_STAGES - 1) % STT_STAGES);
-        }
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         mbar_wait(smem_u32(bars + st), parity);
         const unsigned char* base = stt_smem + (size_t)st * STT_STAGE_BYTES;
         const double* cd = reinterpret_cast<const double*>(base);
         const long long i = i0 + tile * STT_ROWS + threadIdx.x;
-        if (i < i1 && base[9 * STT_ROWS * 8 + threadIdx.x] != 0) {
-            const int q = threadIdx.x;
-            Vec3 x = {cd[q], cd[STT_ROWS + q], cd[2 * STT_ROWS + q]};
-            Vec3 p = {cd[3 * STT_ROWS + q], cd[4 * STT_ROWS + q], cd[5 * STT_ROWS + q]};
-            double t = cd[6 * STT_ROWS + q], s = cd[7 * STT_ROWS + q];
-            const double r0 = cd[8 * STT_ROWS + q];
+        const int q = threadIdx.x;
+        const bool live = i < i1 && base[9 * STT_ROWS * 8 + q] != 0;
+        Vec3 x = {cd[q], cd[STT_ROWS + q], cd[2 * STT_ROWS + q]};
+        Vec3 p = {cd[3 * STT_ROWS + q], cd[4 * STT_ROWS + q], cd[5 * STT_ROWS + q]};
+        double t = cd[6 * STT_ROWS + q], s = cd[7 * STT_ROWS + q];
+        const double r0 = cd[8 * STT_ROWS + q];
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(bars + STT_STAGES + st));     // this warp's rows are in registers
+        if (live) {
             const double r = FIRST ? (cheb3 ? wf_setr_cheb3<SP>(P, T, S.ratebound, cut, p) : setr<SP>(P, S, p)) : r0;          // advance_init!
             const double trem = P.tfinal - t;
             if (!(trem > DBL_EPS)) {                                  // nothing to do this step (:66)
@@ -525,7 +550,6 @@ __global__ void __launch_bounds__(STT_ROWS, 3) k_advance_stream_tma(const __grid
                 if (FIRST && r != r0) Q.col[COL_R][i] = r;
             }
         }
-        __syncthreads();              // every thread has read its row: the stage may be overwritten by the next bulk copies
         if (++st == STT_STAGES) { st = 0; parity ^= 1u; }
     }
     for (int off = 16; off > 0; off >>= 1) nsub += __shfl_down_sync(0xffffffffu, nsub, off);

@@ -257,6 +257,14 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
     return jsel;
 }
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+
 // The OTHER unit (rare processes: the whole collide() + apply!; also the block-coasting of below-cut particles) as a
 // function of its own.  Inlined it is ~2000 instructions of cold code in the middle of the kernel body, between the STEP
 // and the RBEB units.  Out of line (WQ_OTHER_OUTLINE, warp-private kernel) it takes scalars only and rebuilds the pool and
@@ -365,13 +373,6 @@ __device__ __forceinline__ void wf_load_unit(const AdvanceParams& P, const Table
 // One work unit of slot `it` (state word `sw`).  Shared by the barrier-synchronous kernel (k_advance_wf) and the
 // queue-driven kernel (k_advance_aq).  `ldmask` = lanes of this warp that execute a LOAD unit right now (they share one
 // atomic on the global row counter).
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-
 // ALOAD (warp-private kernel only): the LOAD unit does not wait for the row — it issues cp.async copies of the twelve
 // column entries straight into the slot and parks the slot in class LOADWAIT; the warp goes on with other classes while
 // HBM answers (the synchronous LOAD was the one long-scoreboard stall of the kernel: 0.55-0.7 warps per issue), and the

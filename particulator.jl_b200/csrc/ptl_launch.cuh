@@ -194,10 +194,10 @@ int32_t launch_advance_s(ptl_context* ctx, const AdvanceParams& A, long long i0,
                 auto k0 = k_advance_stream_tma<SP, false>;
                 cudaFuncSetAttribute(first ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);   // per device, see launch_advance_t
                 long long tiles = (i1 - i0 + STT_ROWS - 1) / STT_ROWS;
-                long long tg = (long long)ctx->sm_count * 3;
+                long long tg = (long long)ctx->sm_count * STT_MINB;
                 if (tg > tiles) tg = tiles;
-                if (first) k1<<<(unsigned)tg, STT_ROWS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
-                else k0<<<(unsigned)tg, STT_ROWS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+                if (first) k1<<<(unsigned)tg, STT_THREADS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
+                else k0<<<(unsigned)tg, STT_THREADS, tsm, ctx->lstream>>>(A, i0, i1, ctx->d_slow_rows[SP], &ctx->d_sc->slow_count[SP]);
             }
         }
         if (tma) {
