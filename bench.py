@@ -438,6 +438,8 @@ def main():
     ap.add_argument("--strong-total", type=int, default=int(os.environ.get("PTL_BENCH_STRONG_TOTAL", 100_000_000)))
     ap.add_argument("--secondary-scale", type=float, default=1.0, help="scale the secondary probe populations (tests use < 1)")
     ap.add_argument("--e2e-shards", type=int, default=int(os.environ.get("PTL_E2E_SHARDS", 12)))
+    ap.add_argument("--e2e-advance-slots", type=int, default=int(os.environ.get("PTL_E2E_ADVANCE_SLOTS", 0)),
+                    help="how many workers of the e2e leg may be inside advance!+droplow! at the same time (0 = all of them)")
     ap.add_argument("--e2e-ramp", type=float, default=float(os.environ.get("PTL_E2E_RAMP", 0.3)),
                     help="relative size of the first and last shard of the e2e leg (1 = equal shards): small shards at both ends shorten "
                          "the time before the first kernel can start and the last download after the last kernel")
@@ -593,6 +595,7 @@ def main():
         host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()}
         del d
         import ctypes as C
+        from particulator_b200._lib import AdvanceStats
         b = ctx.backend
 
         def ptr(tn, ty, off=0):
@@ -619,6 +622,7 @@ def main():
             wctx = P.Context(device=local_rank)                       # own non-blocking stream
             wmp, wel, wph, wpo = make_world(P, wctx, tables, shard_cap, max(shard_cap // 3, 1 << 20), max(shard_cap // 16, 1 << 18))
             wctx.set_rng(0, 0)
+            wctx.set_profiling(True)
             workers.append((wctx, wmp, wel, psh.desc(wctx)))
         got_rows = [0] * nshards
         out_cap = [int(1.3 * (bounds[k + 1] - bounds[k])) + 4096 for k in range(nshards)]
@@ -627,6 +631,15 @@ def main():
         errors = []
 
         phase_ms = [[0.0, 0.0, 0.0] for _ in range(nworkers)]      # upload / advance+droplow / download wall time per worker (last step)
+        timeline = []                                               # (worker, shard, t_upload, t_advance, t_download, t_end) of the last step, ms
+        step_t0 = [0.0]
+
+        # The main kernel of a shard fills every SM, so the kernels of different workers run one after the other whatever the
+        # host does.  Unthrottled, the short newborn passes of worker A queue behind the main kernels B and C launched in the
+        # meantime, all workers end their advance! together and then copy together while the GPU idles (shard timeline in the
+        # record).  A semaphore lets only `slots` workers into advance! at a time; the others use the wait for their copies.
+        slots = args.e2e_advance_slots if args.e2e_advance_slots > 0 else nworkers
+        adv_sem = threading.Semaphore(slots)
 
         def work(wk):
             wctx, wmp, wel, pd = workers[wk]
@@ -639,12 +652,16 @@ def main():
                                              ptr(host["w"], C.c_double, lo), ptr(host["t"], C.c_double, lo), ptr(host["s"], C.c_double, lo),
                                              ptr(host["r"], C.c_double, lo), ptr(host["active"], C.c_uint8, lo), ptr(host["uid"], C.c_uint64, lo))
                     assert rc == 0, rc
-                    tp1 = time.perf_counter()
-                    rc = b.advance(wctx.h, wmp.id, C.byref(pd), t_loc, None)
-                    assert rc >= 0, rc
-                    for q in wmp:
-                        b.droplow(wctx.h, q.id, 0.0)
-                    tp2 = time.perf_counter()
+                    with adv_sem:
+                        tp1 = time.perf_counter()
+                        rc = b.advance(wctx.h, wmp.id, C.byref(pd), t_loc, None)
+                        assert rc >= 0, rc
+                        for q in wmp:
+                            b.droplow(wctx.h, q.id, 0.0)
+                        wctx.synchronize()
+                        tp2 = time.perf_counter()
+                    ast_ = AdvanceStats()
+                    b.last_advance_stats(wctx.h, C.byref(ast_))
                     o = out[sh]
                     got_rows[sh] = int(b.population_download(wctx.h, wel.id, out_cap[sh], ptr(o["x"], C.c_double), ptr(o["p"], C.c_double),
                                                              ptr(o["w"], C.c_double), ptr(o["t"], C.c_double), ptr(o["s"], C.c_double),
@@ -652,6 +669,9 @@ def main():
                     assert got_rows[sh] > 0
                     tp3 = time.perf_counter()
                     phase_ms[wk][0] += (tp1 - tp0) * 1e3; phase_ms[wk][1] += (tp2 - tp1) * 1e3; phase_ms[wk][2] += (tp3 - tp2) * 1e3
+                    timeline.append((wk, sh, round((tp0 - step_t0[0]) * 1e3, 1), round((tp1 - step_t0[0]) * 1e3, 1),
+                                     round((tp2 - step_t0[0]) * 1e3, 1), round((tp3 - step_t0[0]) * 1e3, 1),
+                                     round(ast_.main_ms, 1), int(ast_.passes)))
                     # photons / positrons born in this shard stay on the device (they are results of later steps' inputs)
                     b.population_clear(wctx.h, list(wmp)[1].id)
                     b.population_clear(wctx.h, list(wmp)[2].id)
@@ -659,6 +679,8 @@ def main():
                 errors.append(repr(exc))
 
         def one_e2e_step():
+            del timeline[:]
+            step_t0[0] = time.perf_counter()
             ths = [threading.Thread(target=work, args=(wk,)) for wk in range(nworkers)]
             for th in ths:
                 th.start()
@@ -687,10 +709,12 @@ def main():
                "h2d_bytes_per_step": 89 * n_e2e, "d2h_bytes_per_step": 89 * d2h_rows // max(args.e2e_steps, 1), "steps": args.e2e_steps,
                "ms_per_step": float(e2e_ms.item()) / max(args.e2e_steps, 1),
                "path": "pinned host arrays -> ptl_population_upload -> ptl_advance -> ptl_droplow -> ptl_population_download, "
-                       f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other; first/last shards {args.e2e_ramp:g}x the middle ones)",
+                       f"{nshards} independent shards through {nworkers} contexts (copies of one overlap the kernels of the other; first/last shards {args.e2e_ramp:g}x the middle ones; {slots} worker(s) inside advance! at a time)",
                "timer": "host wall clock between device-wide synchronizes (work spans several streams)",
                "worker_phase_ms_last_step": {"upload": [round(p[0], 1) for p in phase_ms], "advance_droplow": [round(p[1], 1) for p in phase_ms],
-                                             "download": [round(p[2], 1) for p in phase_ms]}}
+                                             "download": [round(p[2], 1) for p in phase_ms]},
+               "shard_timeline_ms_last_step": {"columns": ["worker", "shard", "upload_start", "advance_start", "download_start", "end", "main_kernel_ms", "passes"],
+                                               "rows": sorted(timeline, key=lambda r: r[2])}}
         for wctx, *_ in workers:
             wctx.close()
 

@@ -36,6 +36,13 @@ constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the s
 #ifndef WF_RBEB_TRIALS
 #define WF_RBEB_TRIALS 0                 // rejection trials evaluated side by side per RBEB unit (0: the sequential two-trial loop)
 #endif
+#ifndef WF_STEP_PHILOX_CALL
+#define WF_STEP_PHILOX_CALL 1               // 1: the STEP unit calls philox_block like every other unit (62 instructions less hot code: main pass 25.2 -> 24.65 ms);
+                                         // 0: the ten rounds inline (round 1: overlapped with the push; measured slower now)
+#endif
+#ifndef WF_STEP_LOG_CALL
+#define WF_STEP_LOG_CALL 0
+#endif
 #ifndef WF_RBEB_LOOP
 #define WF_RBEB_LOOP 5                   // sequential rejection trials per RBEB unit before the slot goes back to the scheduler (see the RBEB unit)
 #endif
@@ -431,9 +438,18 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
             const uint32_t ic = S.idx[it];
             sp_idx = ic + (ic & 1u);                    // every collision test starts on an even draw index
             uint32_t o4[4];
+#if WF_STEP_PHILOX_CALL      // the out-of-line copy every other unit uses: 62 instructions less hot code, one call more on the chain
+            { const uint4 ob = philox_block(sp_idx >> 1, rc.step, rc.seed_lo, rc.seed_hi, (uint32_t)uid, (uint32_t)(uid >> 32) ^ DOM_COLLISION);
+              o4[0] = ob.x; o4[1] = ob.y; o4[2] = ob.z; o4[3] = ob.w; }
+#else
             philox4x32_10(sp_idx >> 1, rc.step, rc.seed_lo, rc.seed_hi, (uint32_t)uid, (uint32_t)(uid >> 32) ^ DOM_COLLISION, o4);
+#endif
             sp_u1 = bits_to_u01(o4[0], o4[1]);
+#if WF_STEP_LOG_CALL
+            sp_snull = -nlog(bits_to_u01(o4[2], o4[3]));
+#else
             sp_snull = -flog_u01(bits_to_u01(o4[2], o4[3]));
+#endif
             sp_o2 = o4[2]; sp_o3 = o4[3];
         }
         Vec3 xo = x, po = p;
@@ -586,6 +602,12 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         RbebConsts k = rbeb_consts(eng, B);
         double w;
         bool acc = false;
+        // WF_RBEB_LOOP sequential trials per unit.  A trial accepts with p ~ 0.27, so an ionisation needs ~3.7 of them.  With
+        // two trials per unit (round 1) 47 % of the entries left the unit accepted: an ionisation cost ~2 scheduling rounds
+        // and ~2 evaluations of rbeb_consts (a logarithm and five divisions), and the tail below ran at 14.6 of 32 lanes —
+        // the SASS page of the ncu capture attributes ~48 % of all executed instructions to ionisations.  Lanes that have
+        // accepted idle while the others go on, but a trial is only ~140 instructions: measured on B200 (4e6 electrons, main
+        // pass, ms) 2 trials 27.8 · 4 trials 26.4 · 5 trials 25.2 · 6 / 8 trials slower again.  Same draws, same results.
 #pragma unroll 1
         for (int q = 0; q < WF_RBEB_LOOP && !acc; q++) {
             double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
