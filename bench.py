@@ -438,12 +438,12 @@ def main():
     ap.add_argument("--strong-total", type=int, default=int(os.environ.get("PTL_BENCH_STRONG_TOTAL", 100_000_000)))
     ap.add_argument("--secondary-scale", type=float, default=1.0, help="scale the secondary probe populations (tests use < 1)")
     ap.add_argument("--e2e-shards", type=int, default=int(os.environ.get("PTL_E2E_SHARDS", 12)))
-    ap.add_argument("--e2e-advance-slots", type=int, default=int(os.environ.get("PTL_E2E_ADVANCE_SLOTS", 0)),
+    ap.add_argument("--e2e-advance-slots", type=int, default=int(os.environ.get("PTL_E2E_ADVANCE_SLOTS", 2)),
                     help="how many workers of the e2e leg may be inside advance!+droplow! at the same time (0 = all of them)")
     ap.add_argument("--e2e-ramp", type=float, default=float(os.environ.get("PTL_E2E_RAMP", 0.3)),
                     help="relative size of the first and last shard of the e2e leg (1 = equal shards): small shards at both ends shorten "
                          "the time before the first kernel can start and the last download after the last kernel")
-    ap.add_argument("--e2e-workers", type=int, default=int(os.environ.get("PTL_E2E_WORKERS", 3)))
+    ap.add_argument("--e2e-workers", type=int, default=int(os.environ.get("PTL_E2E_WORKERS", 4)))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)

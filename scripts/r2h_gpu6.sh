@@ -12,3 +12,4 @@ echo "== launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-
 echo "== full capture: electron first pass"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_advance_wq -s 3 -c 1 -o gpurun_out/r2f_wq_full -f $B > gpurun_out/r2f_ncu_full.log 2>&1; tail -1 gpurun_out/r2f_ncu_full.log | cut -c1-200
 echo "== full capture: electron streaming (kappa ~ 1)"; timeout 600 ncu --set full --clock-control none -k regex:k_advance_stream -s 2 -c 1 -o gpurun_out/r2f_electron_stream_full -f python scripts/kappa_sweep.py 10000000 one > gpurun_out/r2f_ncu_estream.log 2>&1; tail -1 gpurun_out/r2f_ncu_estream.log | cut -c1-200
 echo "== kappa sweep"; timeout 900 python scripts/kappa_sweep.py 10000000 > gpurun_out/r2f_kappa_sweep.jsonl 2> gpurun_out/r2f_kappa.err; cut -c1-200 gpurun_out/r2f_kappa_sweep.jsonl
+echo "== full capture: photon streaming"; timeout 600 ncu --set full --clock-control none -k regex:k_advance_stream -s 2 -c 1 -o gpurun_out/r2f_photon_stream_full -f python scripts/perf_probe.py --species photon --n 20000000 --steps 3 > gpurun_out/r2f_ncu_photon.log 2>&1; tail -1 gpurun_out/r2f_ncu_photon.log | cut -c1-200
