@@ -19,6 +19,9 @@ ap.add_argument("--kernel", type=int, default=5)
 ap.add_argument("--n", type=int, default=50000)
 ap.add_argument("--small-pass", type=int, default=0)
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--dt-scale", type=float, default=1.0, help="scale of dt = 2.5e-11 s; 1/2048 gives kappa ~ 1, so that from the second "
+                "advance! on the leptons take the streaming kernels")
+ap.add_argument("--stream-tma", type=int, default=0, help="1: the TMA-staged lepton streaming kernel")
 a = ap.parse_args()
 co = P.co
 comp = P.air_composition()
@@ -29,14 +32,15 @@ tables = {"electron": P.build_electron_collision_table(comp, Fdt, safety=1.15),
 ctx = P.Context(device=0)
 ctx.set_option("kernel", a.kernel)
 ctx.set_option("small_pass_rows", a.small_pass)
+ctx.set_option("stream_tma", a.stream_tma)
 ctx.set_rng(1, 0)
 mp, el, ph, po = make_world(ctx, tables, a.n, a.n // 2, a.n // 10, cap=4 * a.n, seed=3)
 t = 0.0
 for _ in range(a.steps):
-    t += 2.5e-11
+    t += 2.5e-11 * a.dt_scale
     P.advance(mp, default_pusher(), t)
     for q in (el, ph, po):
         P.droplow(q)
 st = P.last_advance_stats(mp)
-print(f"kernel {a.kernel} small_pass {a.small_pass}: n = {[len(q) for q in (el, ph, po)]}, substeps {st['substeps']}, passes {st['passes']}, flags {ctx.error_flags()}")
+print(f"kernel {a.kernel} small_pass {a.small_pass} dt_scale {a.dt_scale:g} stream_tma {a.stream_tma}: n = {[len(q) for q in (el, ph, po)]}, substeps {st['substeps']}, passes {st['passes']}, flags {ctx.error_flags()}")
 ctx.close()
