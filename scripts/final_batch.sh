@@ -1,5 +1,6 @@
 #!/bin/bash
-# session-3 batch 6 (final tree): streaming kernels, full GPU test suite, the driver's bench commands, ncu evidence
+# One GPU-box batch on the final tree of a round: streaming kernels, full GPU test suite, the driver's bench commands, ncu evidence
+# (outputs gpurun_out/r2f_*; the summaries copied to profiles/r2_final_* come from here)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 echo "== kappa ~ 1: plain"; timeout 200 python scripts/kappa_sweep.py 10000000 one 2>&1 | tail -1 | cut -c1-420
