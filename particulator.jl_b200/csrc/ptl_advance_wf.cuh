@@ -36,6 +36,9 @@ constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the s
 #ifndef WF_RBEB_TRIALS
 #define WF_RBEB_TRIALS 0                 // rejection trials evaluated side by side per RBEB unit (0: the sequential two-trial loop)
 #endif
+#ifndef WF_QUAD_SELECT
+#define WF_QUAD_SELECT 0
+#endif
 #ifndef WF_STEP_PHILOX_CALL
 #define WF_STEP_PHILOX_CALL 1               // 1: the STEP unit calls philox_block like every other unit (62 instructions less hot code: main pass 25.2 -> 24.65 ms);
                                          // 0: the ten rounds inline (round 1: overlapped with the push; measured slower now)
@@ -176,6 +179,25 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
         const double* c = cum + WF_CUM_STRIDE * pre.i;
         const double ca = pre.a, cb = pre.b;
 #define WF_CUMJ(j) fma(c[32 + (j)], cb, fma(c[16 + (j)], ca, c[(j)]))
+#if WF_QUAD_SELECT
+        // Two levels of THREE independent probes (entries 3, 7, 11, then the first three of the quarter that holds xi0)
+        // instead of four dependent ones + the two guard-band entries: the same six evaluations, the same bits, two
+        // shared-memory round trips on the warp's critical path instead of six.
+        const double e3 = WF_CUMJ(3), e7 = WF_CUMJ(7), e11 = WF_CUMJ(11);
+        const int q4 = (!(e3 > xi0) ? 4 : 0) + (!(e7 > xi0) ? 4 : 0) + (!(e11 > xi0) ? 4 : 0);      // monotone: 0, 4, 8 or 12
+        const double f0 = WF_CUMJ(q4), f1 = WF_CUMJ(q4 + 1), f2 = WF_CUMJ(q4 + 2);
+        const int inq = (!(f0 > xi0) ? 1 : 0) + (!(f1 > xi0) ? 1 : 0) + (!(f2 > xi0) ? 1 : 0);     // entries of the quarter that are <= xi0
+        int j = q4 + inq;                                      // entries 0..14 examined: j = how many are <= xi0
+        // the entry at j (first one above xi0) and the one below it are among the evaluated ones, except entry 15
+        const double top = q4 == 0 ? e3 : (q4 == 4 ? e7 : e11);                 // entry q4 + 3 (only used when q4 < 12)
+        double dj = (inq == 0 ? f0 : (inq == 1 ? f1 : (inq == 2 ? f2 : (q4 < 12 ? top : WF_CUMJ(15))))) - xi0;
+        const bool over = np > 15 && j == 15 && !(dj > 0);                      // all sixteen entries are <= xi0: null collision
+        const double below = q4 == 4 ? e3 : (q4 == 8 ? e7 : e11);               // entry q4 - 1 (only used when q4 > 0)
+        const double dp = over ? dj : (inq == 0 ? (q4 > 0 ? below : f0) : (inq == 1 ? f0 : (inq == 2 ? f1 : f2))) - xi0;
+        if (over) { j = 16; dj = INFINITY; }
+        nearb = (fabs(dj) < guard) | (fabs(dp) < guard) | !((T.mono_mask >> pre.i) & 1ULL);
+        jsel = j < np ? j : -1;
+#else
         int j = !(WF_CUMJ(7) > xi0) ? 8 : 0;
         j += !(WF_CUMJ(j + 3) > xi0) ? 4 : 0;
         j += !(WF_CUMJ(j + 1) > xi0) ? 2 : 0;
@@ -186,6 +208,7 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
         if (j == 16) dj = INFINITY;
         nearb = (fabs(dj) < guard) | (fabs(dp) < guard) | !((T.mono_mask >> pre.i) & 1ULL);
         jsel = j < np ? j : -1;
+#endif
 #undef WF_CUMJ
     } else if (TK == 0) {
 #else
