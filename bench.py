@@ -168,6 +168,22 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+def shard_bounds(n, nshards, nworkers, ramp):
+    """Row boundaries of the e2e shards.  Shard sizes ramp up over the first `nworkers` shards and down over the last ones
+    (pipeline fill / drain): nothing can overlap the upload of the very first shard or the download of the very last one,
+    so those are kept small (`ramp` x the middle ones; equal shards when ramp >= 1 or there are too few shards)."""
+    wts = [1.0] * nshards
+    if nshards >= 3 * nworkers and 0 < ramp < 1:
+        for k in range(nworkers):
+            f = ramp + (1 - ramp) * k / nworkers
+            wts[k] = f
+            wts[nshards - 1 - k] = f
+    cum = np.concatenate([[0.0], np.cumsum(wts)]) / sum(wts)
+    bounds = [int(round(n * c)) for c in cum]
+    bounds[0], bounds[-1] = 0, n
+    return bounds
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -605,17 +621,7 @@ def main():
         # their own library contexts: while one context advances a shard, the other one's H2D / D2H copies run on the
         # copy engines.  Every byte still crosses PCIe inside the timed region.
         nshards, nworkers = max(args.e2e_shards, 1), max(args.e2e_workers, 1)
-        # shard sizes ramp up over the first `nworkers` shards and down over the last ones (pipeline fill / drain): nothing can
-        # overlap the upload of the very first shard or the download of the very last one, so those are kept small
-        wts = [1.0] * nshards
-        if nshards >= 3 * nworkers and 0 < args.e2e_ramp < 1:
-            for k in range(nworkers):
-                f = args.e2e_ramp + (1 - args.e2e_ramp) * k / nworkers
-                wts[k] = f
-                wts[nshards - 1 - k] = f
-        cum = np.concatenate([[0.0], np.cumsum(wts)]) / sum(wts)
-        bounds = [int(round(n_e2e * c)) for c in cum]
-        bounds[0], bounds[-1] = 0, n_e2e
+        bounds = shard_bounds(n_e2e, nshards, nworkers, args.e2e_ramp)
         shard_cap = int(1.7 * max(bounds[k + 1] - bounds[k] for k in range(nshards))) + 8192
         workers = []
         for wk in range(nworkers):

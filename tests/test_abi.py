@@ -64,3 +64,22 @@ def test_package_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(txt), f
+
+
+def test_bench_shard_bounds_partition_the_rows():
+    """bench.py's e2e leg cuts the host arrays into shards: every row in exactly one shard, small shards at both ends."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, ns, nw, ramp in ((100_000_007, 12, 4, 0.3), (1000, 12, 3, 0.3), (12345, 10, 4, 0.3), (7, 12, 4, 0.3), (5_000_000, 16, 4, 1.0)):
+        b = bench.shard_bounds(n, ns, nw, ramp)
+        assert len(b) == ns + 1 and b[0] == 0 and b[-1] == n
+        assert all(b[k] <= b[k + 1] for k in range(ns))
+        sizes = [b[k + 1] - b[k] for k in range(ns)]
+        assert sum(sizes) == n
+        if ns >= 3 * nw and ramp < 1 and n > 100 * ns:
+            mid = sizes[ns // 2]
+            assert sizes[0] < 0.5 * mid and sizes[-1] < 0.5 * mid
+            assert all(abs(sizes[k] - mid) <= 2 for k in range(nw, ns - nw))
