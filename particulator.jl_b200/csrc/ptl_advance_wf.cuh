@@ -36,6 +36,9 @@ constexpr int WF_CUM_STRIDE = 50;        // doubles per energy interval of the s
 #ifndef WF_RBEB_TRIALS
 #define WF_RBEB_TRIALS 0                 // rejection trials evaluated side by side per RBEB unit (0: the sequential two-trial loop)
 #endif
+#ifndef WF_RBEB_DYN_MIN
+#define WF_RBEB_DYN_MIN 0
+#endif
 #ifndef WF_QUAD_SELECT
 #define WF_QUAD_SELECT 0
 #endif
@@ -633,12 +636,26 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         // the SASS page of the ncu capture attributes ~48 % of all executed instructions to ionisations.  Lanes that have
         // accepted idle while the others go on, but a trial is only ~140 instructions: measured on B200 (4e6 electrons, main
         // pass, ms) 2 trials 27.8 · 4 trials 26.4 · 5 trials 25.2 · 6 / 8 trials slower again.  Same draws, same results.
+#if WF_RBEB_DYN_MIN > 0
+        // up to WF_RBEB_LOOP trials, but the warp leaves the loop as soon as fewer than WF_RBEB_DYN_MIN of its lanes still need one
+#pragma unroll 1
+        for (int q = 0; q < WF_RBEB_LOOP; q++) {
+            if (!acc) {
+                double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+                double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
+                acc = rbeb_trial(k, u, u2, w);
+            }
+            const unsigned inloop = __activemask();
+            if (__popc(__ballot_sync(inloop, !acc)) < WF_RBEB_DYN_MIN) break;
+        }
+#else
 #pragma unroll 1
         for (int q = 0; q < WF_RBEB_LOOP && !acc; q++) {
             double u = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
             double u2 = rng.u(rc.step, rc.seed_lo, rc.seed_hi);
             acc = rbeb_trial(k, u, u2, w);
         }
+#endif
         wf_store_rng(S, it, rng);
 #endif
         if (!acc) break;                  // stays an RBEB item: more trials next round
