@@ -637,7 +637,9 @@ __device__ __forceinline__ void wf_execute_unit(const AdvanceParams& P, const Ta
         // accepted idle while the others go on, but a trial is only ~140 instructions: measured on B200 (4e6 electrons, main
         // pass, ms) 2 trials 27.8 · 4 trials 26.4 · 5 trials 25.2 · 6 / 8 trials slower again.  Same draws, same results.
 #if WF_RBEB_DYN_MIN > 0
-        // up to WF_RBEB_LOOP trials, but the warp leaves the loop as soon as fewer than WF_RBEB_DYN_MIN of its lanes still need one
+        // up to WF_RBEB_LOOP trials, but the warp leaves the loop as soon as fewer than WF_RBEB_DYN_MIN of its lanes still need one.
+        // Measured slower than the fixed five trials (24.6 ms): at most 8 trials / leave below 8 lanes 26.9, below 12 lanes 27.4,
+        // at most 10 / below 5 lanes 27.3 — the ballot in the loop and the longer worst case cost more than the idle iterations.
 #pragma unroll 1
         for (int q = 0; q < WF_RBEB_LOOP; q++) {
             if (!acc) {
