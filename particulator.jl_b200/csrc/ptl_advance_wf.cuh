@@ -186,8 +186,9 @@ __device__ __forceinline__ int wf_select(const AdvanceParams& P, const TableView
         // Two levels of THREE independent probes (entries 3, 7, 11, then the first three of the quarter that holds xi0)
         // instead of four dependent ones + the two guard-band entries: the same six evaluations, the same bits, two
         // shared-memory round trips on the warp's critical path instead of six.  Measured 15 % SLOWER (28.5 against 24.8 ms,
-        // main pass of 4e6 electrons; the full 16-entry scan WF_LINEAR_SELECT: 28.5 as well): six live doubles and the
-        // selects cost registers the STEP unit does not have at the 128-register cap.
+        // main pass of 4e6 electrons; the full 16-entry scan WF_LINEAR_SELECT: 28.5 as well) — and not for lack of registers:
+        // with 12 warps x 168 registers it is 29.2 against 25.3 ms.  The select logic on six live values costs more than the
+        // four saved round trips, which other warps were hiding anyway.
         const double e3 = WF_CUMJ(3), e7 = WF_CUMJ(7), e11 = WF_CUMJ(11);
         const int q4 = (!(e3 > xi0) ? 4 : 0) + (!(e7 > xi0) ? 4 : 0) + (!(e11 > xi0) ? 4 : 0);      // monotone: 0, 4, 8 or 12
         const double f0 = WF_CUMJ(q4), f1 = WF_CUMJ(q4 + 1), f2 = WF_CUMJ(q4 + 2);

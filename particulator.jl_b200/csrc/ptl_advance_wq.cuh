@@ -12,7 +12,8 @@
 //     REDUX adds on byte-packed counters, the warp picks ONE class (most pending entries, plus an age bonus so that rare
 //     classes — finished particles waiting for write-back, bremsstrahlung — cannot starve), compacts up to 32 slot ids
 //     of that class through 64 bytes of shared memory (ballot + popc prefix), and executes that unit with all lanes
-//     coherent.  ~45 scheduler instructions per round instead of ~250;
+//     coherent.  181 scheduler instructions per round in SASS (ncu source page; the first estimate here said ~45), 19 % of
+//     what the kernel executes; the attempts to shrink them are below (WQ_FULL_RECOUNT=0);
 //   * with all WQ_K x 32 slots always pending in one of three busy classes (STEP, COULOMB, RBEB) the fullest class
 //     holds >= 1/3 of them and, because the classes that are not picked only grow, chunks run at 28-32 lanes.
 // Work units, arithmetic, draw order and Philox streams are those of k_advance_wf (shared wf_execute_unit), so results
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(WQ_THREADS, WQ_MIN_BLOCKS) k_advance_wq(const 
     __syncthreads();                                                                // the table is staged; last CTA-wide barrier
 
     // Scheduler state is lane-parallel: lane c (c < 6) owns class c — its population, its score, its age (rounds a
-    // non-empty class has been passed over).  Decisions are one REDUX each, so a round costs ~30 scheduler instructions
-    // next to the ~500 of a work unit (the first version evaluated every class in every lane: 22 % of all instructions).
+    // non-empty class has been passed over).  Decisions are one REDUX each (the first version evaluated every class in every
+    // lane: 22 % of all instructions).
     int age = 0;
     unsigned round = 0;
     const int myc = lane < WS_IDLE ? lane : 0;
