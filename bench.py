@@ -653,6 +653,8 @@ def main():
             try:
                 for sh in range(wk, nshards, nworkers):
                     lo, m = bounds[sh], bounds[sh + 1] - bounds[sh]
+                    if m <= 0:                                         # tiny runs: a ramped shard may be empty
+                        continue
                     tp0 = time.perf_counter()
                     rc = b.population_upload(wctx.h, wel.id, m, ptr(host["x"], C.c_double, lo), ptr(host["p"], C.c_double, lo),
                                              ptr(host["w"], C.c_double, lo), ptr(host["t"], C.c_double, lo), ptr(host["s"], C.c_double, lo),
